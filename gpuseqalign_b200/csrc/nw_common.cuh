@@ -1,0 +1,133 @@
+// nw_common.cuh -- shared device helpers for the B200 NW engine (sm_100a only).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 900)
+#error "gpuseqalign_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace nwb {
+
+constexpr int kWarp = 32;
+constexpr int kMaxLetters = 63;       // substitution alphabet limit (reference uses 25)
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- DPX / integer-pipe primitives -------------------------------------------------------
+// One cell of the recurrence in "shifted" coordinates P[i][j] = H[i][j] - (i+j)*gap
+// (the reference's own half-way form is nwalign_gpu1_ml_diag.cu:65-70):
+//     P[i][j] = max3(P[i-1][j-1] + s', P[i-1][j], P[i][j-1]),   s' = max(subst - 2*gap, 0)
+// s' is fetched as one byte of a packed profile word and added with IDP.4A (fma pipe), the
+// 3-way max is a single VIMNMX3 (alu pipe): two issue slots per cell on two different pipes.
+__device__ __forceinline__ int add_byte(unsigned word, unsigned onehot, int acc)
+{
+    return (int)__dp4a(word, onehot, (unsigned)acc);      // IDP.4A.U8.U8
+}
+__device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }   // VIMNMX3
+
+// ---- inter-CTA flags ---------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_volatile(const int* p)
+{
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// ---- tagged 64-bit elements: value and ready-flag in ONE naturally atomic store -------------
+__device__ __forceinline__ unsigned long long pack_tagged(int v, unsigned tag)
+{
+    return ((unsigned long long)tag << 32) | (unsigned)v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// returns the value once its tag matches; `first` is an earlier (prefetched) read of *p
+__device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned long long first, unsigned tag)
+{
+    unsigned long long v = first;
+    while ((unsigned)(v >> 32) != tag) {
+        __nanosleep(20);
+        v = ld_relaxed64(p);
+    }
+    return (int)(unsigned)v;
+}
+
+// same, but a miss first sleeps `backoff_ns`: the consumer drops behind its producer once and its
+// later (prefetched) reads hit, instead of re-polling L2 on the critical path of every chunk
+__device__ __forceinline__ int wait_tagged_backoff(const unsigned long long* p, unsigned long long first, unsigned tag, unsigned backoff_ns,
+                                                   unsigned& spins)
+{
+    unsigned long long v = first;
+    if (backoff_ns == 0xffffffffu) return (int)(unsigned)v;     // timing experiment only: no dependency on the band above
+    if ((unsigned)(v >> 32) != tag) {
+        __nanosleep(backoff_ns);
+        v = ld_relaxed64(p);
+        spins += 0x10001u;
+        while ((unsigned)(v >> 32) != tag) {
+            __nanosleep(50);
+            v = ld_relaxed64(p);
+            spins += 1u;
+        }
+    }
+    return (int)(unsigned)v;
+}
+
+// streaming (evict-first) global accesses for header traffic that is written once / read once
+__device__ __forceinline__ void st_cs(int* p, int v) { __stcs(p, v); }
+__device__ __forceinline__ void st_cs4(int4* p, int4 v) { __stcs(p, v); }
+
+// ---- TMA-style bulk copy global -> shared (cp.async.bulk + mbarrier), used for sequence windows
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+}  // namespace nwb

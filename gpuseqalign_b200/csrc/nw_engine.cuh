@@ -1,0 +1,94 @@
+// nw_engine.cuh -- host-side engine state behind the C ABI (include/nwb200.h).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cuda_runtime.h>
+#include "../../include/nwb200.h"
+
+namespace nwb {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Geometry {
+    int R = 4, W = 4, K = 2;
+    int By = 512, Bx = 512;
+    int n = 0, m = 0;
+    int trows = 0, tcols = 0;
+    int nlc = 0;
+    long long ldr = 0, ldc = 0;
+    long long npad = 0;
+};
+
+}  // namespace nwb
+
+struct nwb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    // scoring
+    std::vector<int32_t> subst;
+    int S = 0;
+    int gap = 0;
+    bool scoring_set = false;
+    int max_sprime = 0;
+    nwb::DevBuf d_sprime, d_subst;
+    // resident pair
+    nwb::Geometry g;
+    bool pair_resident = false;
+    bool headers_valid = false;
+    bool fill_done = false;
+    nwb::DevBuf d_y, d_x, d_HR, d_HC, d_lastcol, d_sync, d_score;
+    nwb::PinBuf h_stage, h_small;
+    // traceback
+    nwb::DevBuf d_exit, d_path, d_ops, d_edit, d_tmeta;
+    bool trace_done = false;
+    // batch
+    nwb::DevBuf d_bletters, d_boffY, d_boffX, d_blenY, d_blenX, d_bscores, d_bsync;
+    size_t batch_pairs = 0;
+    bool batch_resident = false;
+    // bookkeeping
+    nwb200_timing timing = {};
+    unsigned epoch = 0;
+    bool debug_stamps = false;
+    unsigned backoff_ns = 1500;
+    int launches = 0;
+    cudaError_t last_cuda = cudaSuccess;
+    std::string last_error;
+};

@@ -1,0 +1,380 @@
+// nwb200_capi.cu -- the C ABI of include/nwb200.h on top of the sm_100a kernels.
+//
+// Host side of the hot path: what NwAlign_Gpu9_Mlsp_DiagDiagDiag's host function does
+// (reference nwalign_gpu9_mlsp_diagdiagdiag.cu:368-722) minus everything that does not need to
+// be inside the timed region: buffers, stream and events live in the context and grow on demand
+// (the reference cudaMallocs, captures and instantiates a CUDA graph inside every align call).
+#include "nw_engine.cuh"
+#include "nw_fill.cuh"
+#include "nw_trace.cuh"
+#include "nw_batch.cuh"
+
+using namespace nwb;
+
+#define NWB_VERSION "nwb200 0.1 (sm_100a)"
+
+namespace {
+
+int fail(nwb200_ctx* c, int stat, const char* msg, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->last_error = msg;
+        if (e != cudaSuccess) { c->last_cuda = e; c->last_error += std::string(": ") + cudaGetErrorString(e); }
+    }
+    return stat;
+}
+
+#define CU(c, call, stat, msg) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((c), (stat), (msg), e__); } while (0)
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// ---------------------------------------------------------------------------------------------
+// geometry: the analogue of nwalign_gpu9_mlsp_diagdiagdiag.cu:384-431
+int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
+{
+    Geometry& g = c->g;
+    int R = 4, W = 4, K = 0, Bx = 512;
+    if (p) {
+        if (p->rows_per_lane) R = p->rows_per_lane;
+        if (p->warps_per_block) W = p->warps_per_block;
+        if (p->tile_cols) Bx = p->tile_cols;
+        if (p->reserved) K = p->reserved;
+    }
+    if (!(R == 4 || R == 8) || !(W == 4 || W == 8) || Bx < 32 || (Bx % 32) != 0 || !(K == 0 || K == 1 || K == 2))
+        return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8}, warps_per_block in {4,8}, tile_cols multiple of 32)");
+    const int By = R * 32 * W;
+    const long long trows = ((long long)n + By - 1) / By;
+    if (K == 0) K = (trows <= 4LL * c->sm_count) ? 2 : 1;     // few bands: latency-bound -> shuffle off the critical path
+    g.R = R; g.W = W; g.K = K; g.By = By; g.Bx = Bx; g.n = n; g.m = m;
+    g.trows = (int)(trows < 1 ? 1 : trows);
+    g.tcols = (m + Bx - 1) / Bx; if (g.tcols < 1) g.tcols = 1;
+    g.nlc = (m + (31 * (R + K - 1) + R - 1) + 31) / 32;      // Sched<R,W,K>::nlc(m)
+    g.ldr = 32LL * g.nlc;
+    g.npad = (long long)g.trows * By;
+    g.ldc = g.npad;
+    return NWB200_SUCCESS;
+}
+
+template <int R, int W, int K>
+int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
+{
+    size_t smem = Sched<R, W, K>::smem_bytes(c->S);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nw_fill_kernel<R, W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(fill)", e);
+    }
+    nw_fill_kernel<R, W, K><<<grid, W * 32, smem, c->stream>>>(a);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel launch", e);
+    return NWB200_SUCCESS;
+}
+
+int launch_fill(nwb200_ctx* c, const FillArgs& a)
+{
+    const Geometry& g = c->g;
+    int per_sm = 2048 / (g.W * 32);
+    if (per_sm > 8) per_sm = 8;
+    long long grid = (long long)c->sm_count * per_sm;
+    if (grid > g.trows) grid = g.trows;
+#define NWB_CASE(R_, W_, K_) if (g.R == R_ && g.W == W_ && g.K == K_) return launch_fill_t<R_, W_, K_>(c, a, (int)grid)
+    NWB_CASE(4, 4, 2); NWB_CASE(4, 4, 1); NWB_CASE(8, 4, 1); NWB_CASE(8, 4, 2);
+    NWB_CASE(4, 8, 2); NWB_CASE(4, 8, 1); NWB_CASE(8, 8, 1); NWB_CASE(8, 8, 2);
+#undef NWB_CASE
+    return fail(c, NWB200_ERR_INVALID_VALUE, "no kernel instance for these tile parameters");
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* nwb200_version(void) { return NWB_VERSION; }
+
+int nwb200_create(nwb200_ctx** out, int device)
+{
+    if (!out) return NWB200_ERR_INVALID_VALUE;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return NWB200_ERR_CUDA_GENERAL;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NWB200_ERR_CUDA_GENERAL;
+    if (prop.major < 10) return NWB200_ERR_CUDA_GENERAL;     // sm_100a code only: no other-arch / CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return NWB200_ERR_CUDA_GENERAL;
+    nwb200_ctx* c = new (std::nothrow) nwb200_ctx();
+    if (!c) return NWB200_ERR_MEMORY_ALLOCATION;
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NWB200_ERR_CUDA_GENERAL; }
+    for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NWB200_ERR_CUDA_GENERAL; }
+    if (c->h_small.ensure(4096) != cudaSuccess) { delete c; return NWB200_ERR_MEMORY_ALLOCATION; }
+    *out = c;
+    return NWB200_SUCCESS;
+}
+
+void nwb200_destroy(nwb200_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_HC, &c->d_lastcol, &c->d_sync, &c->d_score,
+                      &c->d_exit, &c->d_path, &c->d_ops, &c->d_edit, &c->d_tmeta,
+                      &c->d_bletters, &c->d_boffY, &c->d_boffX, &c->d_blenY, &c->d_blenX, &c->d_bscores, &c->d_bsync})
+        b->release();
+    c->h_stage.release(); c->h_small.release();
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int nwb200_set_scoring(nwb200_ctx* c, const int32_t* subst, int substsz, int gap)
+{
+    if (!c || !subst || substsz < 1 || substsz > kMaxLetters) return fail(c, NWB200_ERR_INVALID_VALUE, "bad substitution matrix size");
+    cudaSetDevice(c->device);
+    const int S = substsz;
+    std::vector<uint8_t> sp((size_t)S * S);
+    int mx = 0;
+    for (int i = 0; i < S * S; i++) {
+        long long v = (long long)subst[i] - 2LL * gap;       // s' = s - 2*gap
+        if (v < 0) v = 0;                                     // exact: a negative s' can never win (P is monotone along rows)
+        if (v > 255) return fail(c, NWB200_ERR_INVALID_VALUE, "subst - 2*gap exceeds the byte profile range (0..255)");
+        sp[i] = (uint8_t)v;
+        if (v > mx) mx = (int)v;
+    }
+    CU(c, c->d_sprime.ensure(sp.size()), NWB200_ERR_MEMORY_ALLOCATION, "alloc sprime");
+    CU(c, c->d_subst.ensure(sizeof(int32_t) * S * S), NWB200_ERR_MEMORY_ALLOCATION, "alloc subst");
+    CU(c, cudaMemcpyAsync(c->d_sprime.p, sp.data(), sp.size(), cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "copy sprime");
+    CU(c, cudaMemcpyAsync(c->d_subst.p, subst, sizeof(int32_t) * S * S, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "copy subst");
+    CU(c, cudaStreamSynchronize(c->stream), NWB200_ERR_MEMORY_TRANSFER, "sync scoring");
+    c->subst.assign(subst, subst + (size_t)S * S);
+    c->S = S; c->gap = gap; c->max_sprime = mx; c->scoring_set = true;
+    c->pair_resident = false; c->batch_resident = false;
+    return NWB200_SUCCESS;
+}
+
+static int check_range(nwb200_ctx* c, long long n, long long m)
+{
+    if (n < 1 || m < 1 || n > 0x7ffffff0LL || m > 0x7ffffff0LL) return fail(c, NWB200_ERR_INVALID_VALUE, "sequence lengths must be in [1, 2^31)");
+    long long mn = n < m ? n : m;
+    long long g = c->gap < 0 ? -(long long)c->gap : c->gap;
+    if (mn * c->max_sprime + (n + m) * g >= 0x7fffffffLL) return fail(c, NWB200_ERR_INVALID_VALUE, "scores would overflow int32");
+    return NWB200_SUCCESS;
+}
+
+static int upload_common(nwb200_ctx* c, const uint8_t* stage_y, long long n, const uint8_t* stage_x, long long m, const nwb200_params* p)
+{
+    int rc = plan_geometry(c, (int)n, (int)m, p);
+    if (rc) return rc;
+    const Geometry& g = c->g;
+    CU(c, c->d_y.ensure((size_t)g.npad + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc y");
+    CU(c, c->d_x.ensure((size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc x");
+    CU(c, cudaEventRecord(c->ev[0], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    CU(c, cudaMemcpyAsync(c->d_y.p, stage_y, (size_t)n, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D y");
+    CU(c, cudaMemcpyAsync(c->d_x.p, stage_x, (size_t)m, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D x");
+    CU(c, cudaEventRecord(c->ev[1], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    c->pair_resident = true; c->headers_valid = false; c->fill_done = false; c->trace_done = false;
+    return NWB200_SUCCESS;
+}
+
+int nwb200_upload_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8_t* x, int64_t m, const nwb200_params* p)
+{
+    if (!c || !y || !x) return fail(c, NWB200_ERR_INVALID_VALUE, "null argument");
+    if (!c->scoring_set) return fail(c, NWB200_ERR_INVALID_VALUE, "nwb200_set_scoring has not been called");
+    cudaSetDevice(c->device);
+    int rc = check_range(c, n, m);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream), NWB200_ERR_CUDA_GENERAL, "sync before staging");
+    CU(c, c->h_stage.ensure((size_t)n + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
+    uint8_t* sy = c->h_stage.as<uint8_t>();
+    uint8_t* sx = sy + n;
+    const int S = c->S;
+    unsigned bad = 0;
+    for (int64_t i = 0; i < n; i++) { uint8_t v = y[i]; bad |= (v >= S); sy[i] = v; }
+    for (int64_t j = 0; j < m; j++) { uint8_t v = x[j]; bad |= (v >= S); sx[j] = v; }
+    if (bad) return fail(c, NWB200_ERR_INVALID_VALUE, "letter index outside the substitution matrix");
+    return upload_common(c, sy, n, sx, m, p);
+}
+
+static int upload_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, const int32_t* seqX, int64_t adjcols, const nwb200_params* p)
+{
+    if (!c || !seqY || !seqX) return fail(c, NWB200_ERR_INVALID_VALUE, "null argument");
+    if (!c->scoring_set) return fail(c, NWB200_ERR_INVALID_VALUE, "nwb200_set_scoring has not been called");
+    cudaSetDevice(c->device);
+    const int64_t n = adjrows - 1, m = adjcols - 1;
+    int rc = check_range(c, n, m);
+    if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream), NWB200_ERR_CUDA_GENERAL, "sync before staging");
+    CU(c, c->h_stage.ensure((size_t)n + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
+    uint8_t* sy = c->h_stage.as<uint8_t>();
+    uint8_t* sx = sy + n;
+    const unsigned S = (unsigned)c->S;
+    unsigned bad = 0;
+    for (int64_t i = 0; i < n; i++) { unsigned v = (unsigned)seqY[i + 1]; bad |= (v >= S); sy[i] = (uint8_t)v; }   // element 0 is the dummy header
+    for (int64_t j = 0; j < m; j++) { unsigned v = (unsigned)seqX[j + 1]; bad |= (v >= S); sx[j] = (uint8_t)v; }
+    if (bad) return fail(c, NWB200_ERR_INVALID_VALUE, "letter index outside the substitution matrix");
+    return upload_common(c, sy, n, sx, m, p);
+}
+
+int nwb200_fill_resident(nwb200_ctx* c, int flags)
+{
+    if (!c || !c->pair_resident) return fail(c, NWB200_ERR_INVALID_VALUE, "no pair resident on the device");
+    cudaSetDevice(c->device);
+    const Geometry& g = c->g;
+    const bool keep = (flags & NWB200_KEEP_HEADERS) != 0;
+    const int ncolh = g.tcols - 1;
+    {
+        const size_t before = c->d_HR.cap;
+        CU(c, c->d_HR.ensure(sizeof(unsigned long long) * (size_t)(g.trows + 1) * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc header rows");
+        if (c->d_HR.cap != before)   // fresh memory may hold anything: clear the tag halves once
+            CU(c, cudaMemsetAsync(c->d_HR.p, 0, c->d_HR.cap, c->stream), NWB200_ERR_CUDA_GENERAL, "memset header rows");
+    }
+    if (keep && ncolh > 0) CU(c, c->d_HC.ensure(sizeof(int) * (size_t)ncolh * (size_t)g.ldc), NWB200_ERR_MEMORY_ALLOCATION, "alloc header columns");
+    CU(c, c->d_lastcol.ensure(sizeof(int) * (size_t)g.npad), NWB200_ERR_MEMORY_ALLOCATION, "alloc last column");
+    CU(c, c->d_sync.ensure(sizeof(int) * 8), NWB200_ERR_MEMORY_ALLOCATION, "alloc ticket");
+    CU(c, cudaEventRecord(c->ev[2], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    CU(c, cudaMemsetAsync(c->d_sync.p, 0, sizeof(int) * 8, c->stream), NWB200_ERR_CUDA_GENERAL, "memset ticket");
+    FillArgs a;
+    a.y = c->d_y.as<uint8_t>(); a.x = c->d_x.as<uint8_t>(); a.n = g.n; a.m = g.m;
+    a.sprime = c->d_sprime.as<uint8_t>(); a.S = c->S;
+    a.HR = c->d_HR.as<unsigned long long>(); a.ldr = g.ldr;
+    a.HC = c->d_HC.as<int>(); a.ldc = g.ldc;
+    a.lastcol = c->d_lastcol.as<int>();
+    c->epoch++;
+    if (c->epoch == 0) c->epoch = 1;
+    a.tag = c->epoch; a.ticket = c->d_sync.as<int>();
+    a.Bx = g.Bx; a.trows = g.trows; a.keep_hdr = keep ? 1 : 0;
+    a.backoff_ns = c->backoff_ns;
+    a.dbg = nullptr;
+    if (c->debug_stamps) {
+        CU(c, c->d_tmeta.ensure(sizeof(unsigned long long) * (4 * (size_t)g.trows + 2400)), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
+        a.dbg = c->d_tmeta.as<unsigned long long>();
+    }
+    int rc = launch_fill(c, a);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(c->ev[3], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    c->fill_done = true; c->headers_valid = keep; c->trace_done = false;
+    return NWB200_SUCCESS;
+}
+
+int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
+{
+    if (!c || !align_cost || !c->fill_done) return fail(c, NWB200_ERR_INVALID_VALUE, "no fill has been run");
+    cudaSetDevice(c->device);
+    const Geometry& g = c->g;
+    int* hs = c->h_small.as<int>();
+    CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    CU(c, cudaMemcpyAsync(hs, c->d_lastcol.as<int>() + (g.n - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
+    CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel execution", e);
+    // un-shift: H[n][m] = P[n][m] + (n+m)*gap
+    *align_cost = (int32_t)((long long)hs[0] + ((long long)g.n + g.m) * c->gap);
+    c->timing.align_cpy_dev = ev_ms(c->ev[0], c->ev[1]);
+    c->timing.align_calc = ev_ms(c->ev[2], c->ev[3]);
+    c->timing.align_cpy_host = ev_ms(c->ev[4], c->ev[5]);
+    return NWB200_SUCCESS;
+}
+
+static void fill_hdr_info(const nwb200_ctx* c, nwb200_hdr_info* h)
+{
+    if (!h) return;
+    const Geometry& g = c->g;
+    h->tile_rows = g.By; h->tile_cols = g.Bx; h->trows = g.trows; h->tcols = g.tcols;
+    h->hrow_elems = (int64_t)g.trows * g.tcols * (1 + g.Bx);
+    h->hcol_elems = (int64_t)g.trows * g.tcols * (1 + g.By);
+}
+
+int nwb200_align_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8_t* x, int64_t m,
+                         const nwb200_params* p, int flags, int32_t* align_cost, nwb200_hdr_info* hdr)
+{
+    int rc = nwb200_upload_pair_u8(c, y, n, x, m, p);
+    if (rc) return rc;
+    rc = nwb200_fill_resident(c, flags);
+    if (rc) return rc;
+    rc = nwb200_fetch_score(c, align_cost);
+    if (rc) return rc;
+    fill_hdr_info(c, hdr);
+    return NWB200_SUCCESS;
+}
+
+int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, const int32_t* seqX, int64_t adjcols,
+                          const nwb200_params* p, int flags, int32_t* align_cost, nwb200_hdr_info* hdr)
+{
+    int rc = upload_pair_i32(c, seqY, adjrows, seqX, adjcols, p);
+    if (rc) return rc;
+    rc = nwb200_fill_resident(c, flags);
+    if (rc) return rc;
+    rc = nwb200_fetch_score(c, align_cost);
+    if (rc) return rc;
+    fill_hdr_info(c, hdr);
+    return NWB200_SUCCESS;
+}
+
+int nwb200_copy_headers(nwb200_ctx* c, int32_t* hrow_host, int32_t* hcol_host)
+{
+    if (!c || !hrow_host || !hcol_host) return fail(c, NWB200_ERR_INVALID_VALUE, "null argument");
+    if (!c->headers_valid) return fail(c, NWB200_ERR_INVALID_VALUE, "the last align did not keep headers (NWB200_KEEP_HEADERS)");
+    cudaSetDevice(c->device);
+    const Geometry& g = c->g;
+    const size_t nrow = (size_t)g.trows * g.tcols * (1 + g.Bx), ncol = (size_t)g.trows * g.tcols * (1 + g.By);
+    CU(c, c->d_edit.ensure(sizeof(int) * (nrow + ncol)), NWB200_ERR_MEMORY_ALLOCATION, "alloc header export");
+    int* d_hrow = c->d_edit.as<int>();
+    int* d_hcol = d_hrow + nrow;
+    CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    {
+        const int threads = 256;
+        size_t total = nrow > ncol ? nrow : ncol;
+        int grid = (int)((total + threads - 1) / threads);
+        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
+        nw_export_headers_kernel<<<grid, threads, 0, c->stream>>>(c->d_HR.as<unsigned long long>(), g.ldr, c->d_HC.as<int>(), g.ldc,
+                                                                   g.n, g.m, g.By, g.Bx, g.trows, g.tcols, c->gap, d_hrow, d_hcol);
+        c->launches++;
+        CU(c, cudaGetLastError(), NWB200_ERR_KERNEL_FAILURE, "export kernel launch");
+    }
+    CU(c, cudaMemcpyAsync(hrow_host, d_hrow, sizeof(int) * nrow, cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H hrow");
+    CU(c, cudaMemcpyAsync(hcol_host, d_hcol, sizeof(int) * ncol, cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H hcol");
+    CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "header export", e);
+    c->timing.align_cpy_host = ev_ms(c->ev[4], c->ev[5]);
+    return NWB200_SUCCESS;
+}
+
+#include "nwb200_capi_trace.inc"
+#include "nwb200_capi_batch.inc"
+
+// developer aid (not part of the public header): per-band globaltimer stamps of the next fills
+NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, long long enable, unsigned long long* out, int max_bands)
+{
+    if (!c) return NWB200_ERR_INVALID_VALUE;
+    c->debug_stamps = (enable & 1) != 0;
+    if (enable >> 8) c->backoff_ns = (unsigned)(enable >> 8);
+    if (out && c->fill_done && c->d_tmeta.p) {
+        int nb = c->g.trows < max_bands ? c->g.trows : max_bands;
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(out, c->d_tmeta.p, sizeof(unsigned long long) * 4 * nb, cudaMemcpyDeviceToHost);
+        if (max_bands >= c->g.trows + 600) cudaMemcpy(out + 4 * (size_t)max_bands, (unsigned long long*)c->d_tmeta.p + 4 * (size_t)c->g.trows, sizeof(unsigned long long) * 2400, cudaMemcpyDeviceToHost);
+        return nb;
+    }
+    return 0;
+}
+
+int nwb200_last_cuda_error(const nwb200_ctx* c) { return c ? (int)c->last_cuda : 0; }
+const char* nwb200_last_error(const nwb200_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+int nwb200_get_timing(const nwb200_ctx* c, nwb200_timing* out)
+{
+    if (!c || !out) return NWB200_ERR_INVALID_VALUE;
+    *out = c->timing;
+    return NWB200_SUCCESS;
+}
+void* nwb200_stream(const nwb200_ctx* c) { return c ? (void*)c->stream : nullptr; }
+int nwb200_sync(nwb200_ctx* c)
+{
+    if (!c) return NWB200_ERR_INVALID_VALUE;
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "stream synchronize", e);
+    return NWB200_SUCCESS;
+}
+int nwb200_kernel_launches(const nwb200_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

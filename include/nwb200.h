@@ -1,0 +1,169 @@
+/*
+ * nwb200.h -- C ABI of the B200-native Needleman-Wunsch (linear gap) engine.
+ *
+ * This is the drop-in boundary for the hot path of markods/GpuSeqAlign: everything the
+ * reference's algorithm plug-ins do between benchmark.cpp:473 (alg.align), :484 (alg.hash)
+ * and :488 (alg.trace).  The C++ adaptor in gpuseqalign_b200/plugin/nwalign_b200.cpp wraps
+ * these calls in the reference's NwAlignFn / NwTraceFn / NwHashFn signatures
+ * (nw_algorithm.hpp:11-13) so the engine registers as one more entry of
+ * getNwAlgorithmMap (nw_algorithm.cpp:48-68); INTEGRATION.md shows the binding.
+ *
+ * Conventions (identical to the reference's data contract, run_types.hpp:70-110):
+ *   - sequences are arrays of letter indices; the *_i32 entry points take the reference's
+ *     `int` vectors with a dummy element 0 in front (adjrows = lenY + 1, adjcols = lenX + 1,
+ *     file_formats.cpp:43-47, benchmark.cpp:411-426); the *_u8 / batch entry points take
+ *     plain byte letters without the dummy element;
+ *   - seqY indexes matrix rows, seqX matrix columns; subst[y * substsz + x] (benchmark.cpp:192);
+ *   - gap is the (normally negative) linear gap score nw.gapoCost (cmd_parser.cpp:302);
+ *   - every function returns an NwStat value (run_types.hpp:12-24): 0 = success,
+ *     2 errorCudaGeneral, 3 errorMemoryAllocation, 4 errorMemoryTransfer, 5 errorKernelFailure,
+ *     8 errorInvalidValue, 9 errorInvalidResult.  Nothing throws across this boundary.
+ *   - a context is not thread-safe; it owns one CUDA device, one stream and all device buffers
+ *     (the reference instead re-allocates inside every timed align, nwalign_gpu9...cu:438-449).
+ *
+ * Results are bit-exact with the reference: integer score, score hash, trace hash and edit
+ * transcript (nwtrace1_plain.cpp / nwtrace2_sparse.cpp semantics).  There is no CPU fallback:
+ * without a CUDA device nwb200_create fails with errorCudaGeneral.
+ */
+#ifndef NWB200_H
+#define NWB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define NWB200_API __attribute__((visibility("default")))
+#else
+#define NWB200_API
+#endif
+
+/* NwStat values (run_types.hpp:12-24). */
+enum {
+    NWB200_SUCCESS = 0,
+    NWB200_ERR_CUDA_GENERAL = 2,
+    NWB200_ERR_MEMORY_ALLOCATION = 3,
+    NWB200_ERR_MEMORY_TRANSFER = 4,
+    NWB200_ERR_KERNEL_FAILURE = 5,
+    NWB200_ERR_INVALID_VALUE = 8,
+    NWB200_ERR_INVALID_RESULT = 9
+};
+
+typedef struct nwb200_ctx nwb200_ctx;
+
+/* Tile geometry: the analogue of the reference's per-algorithm parameters
+ * (param_best.json: subtileRows/subtileCols/subtileBx for gpu9; nwalign_gpu9...cu:384-398).
+ * tile_rows is fixed by the kernel shape (rows per lane x 32 lanes x warps per block);
+ * tile_cols is the header-column spacing, a multiple of 32.  0 = engine default. */
+typedef struct nwb200_params {
+    int32_t rows_per_lane;   /* 4 (default) or 8 */
+    int32_t warps_per_block; /* 1..8, default 4   */
+    int32_t tile_cols;       /* header column spacing Bx, multiple of 32, default 512 */
+    int32_t reserved;
+} nwb200_params;
+
+/* Flags for nwb200_align_pair_*. */
+#define NWB200_SCORE_ONLY   0x0   /* keep only what the score needs                        */
+#define NWB200_KEEP_HEADERS 0x1   /* keep tile header rows/columns for trace / copy_headers */
+
+/* Geometry of the sparse score-matrix representation kept on the device after an align
+ * (what the reference publishes in nw.tileHdrMatRows/Cols, tileHrowLen/tileHcolLen,
+ * nwalign_gpu9...cu:696-699). */
+typedef struct nwb200_hdr_info {
+    int32_t tile_rows;     /* By */
+    int32_t tile_cols;     /* Bx */
+    int32_t trows;         /* tileHdrMatRows */
+    int32_t tcols;         /* tileHdrMatCols */
+    int64_t hrow_elems;    /* trows*tcols*(1+Bx) ints in the reference layout */
+    int64_t hcol_elems;    /* trows*tcols*(1+By) */
+} nwb200_hdr_info;
+
+/* Per-phase device/host times of the last call, in ms (the reference's Stopwatch lap names,
+ * file_formats.cpp:505-518). */
+typedef struct nwb200_timing {
+    float align_cpy_dev;   /* H2D of the sequences                     */
+    float align_calc;      /* fill kernel(s), CUDA events              */
+    float align_cpy_host;  /* D2H of the score (and headers if copied) */
+    float trace_calc;      /* traceback kernels, CUDA events           */
+    float trace_cpy_host;  /* D2H of the transcript                    */
+} nwb200_timing;
+
+NWB200_API int  nwb200_create(nwb200_ctx** out, int device);
+NWB200_API void nwb200_destroy(nwb200_ctx* ctx);
+
+/* Replaces initNwInput's subst upload + gapoCost (benchmark.cpp:185-220). */
+NWB200_API int  nwb200_set_scoring(nwb200_ctx* ctx, const int32_t* subst, int substsz, int gap);
+
+/* Replaces NwAlign_Gpu9_Mlsp_DiagDiagDiag (nwalign_gpu9_mlsp_diagdiagdiag.cu:368-722):
+ * H2D of the two sequences, score-matrix fill on the GPU, align_cost back on the host. */
+NWB200_API int  nwb200_align_pair_i32(nwb200_ctx* ctx, const int32_t* seqY, int64_t adjrows,
+                                      const int32_t* seqX, int64_t adjcols,
+                                      const nwb200_params* params /* nullable */, int flags,
+                                      int32_t* align_cost, nwb200_hdr_info* hdr /* nullable */);
+/* Same with byte letters (no dummy element). */
+NWB200_API int  nwb200_align_pair_u8(nwb200_ctx* ctx, const uint8_t* y, int64_t len_y,
+                                     const uint8_t* x, int64_t len_x,
+                                     const nwb200_params* params, int flags,
+                                     int32_t* align_cost, nwb200_hdr_info* hdr);
+
+/* Split form used by the benchmark to time the device part with inputs resident in HBM:
+ * upload once, then (re)run fill / trace any number of times. */
+NWB200_API int  nwb200_upload_pair_u8(nwb200_ctx* ctx, const uint8_t* y, int64_t len_y,
+                                      const uint8_t* x, int64_t len_x, const nwb200_params* params);
+NWB200_API int  nwb200_fill_resident(nwb200_ctx* ctx, int flags);            /* async on the ctx stream */
+NWB200_API int  nwb200_trace_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
+NWB200_API int  nwb200_fetch_score(nwb200_ctx* ctx, int32_t* align_cost);    /* syncs */
+NWB200_API int  nwb200_fetch_trace(nwb200_ctx* ctx, char* edit_buf, size_t cap, size_t* len,
+                                   uint32_t* trace_hash);                    /* syncs */
+
+/* Replaces NwTrace2_Sparse (nwtrace2_sparse.cpp:102-257) for the pair of the last
+ * align call made with NWB200_KEEP_HEADERS: tile recompute + walk on the GPU.
+ * edit_buf receives the run-length transcript ("<count><op>..." with ops = X I D,
+ * nwtrace1_plain.cpp:81-103), not NUL-terminated; *len its length.  If cap is too small
+ * the call returns NWB200_ERR_INVALID_VALUE and *len holds the required size. */
+NWB200_API int  nwb200_trace_pair(nwb200_ctx* ctx, char* edit_buf, size_t cap, size_t* len,
+                                  uint32_t* trace_hash);
+
+/* Replaces the D2H of both header matrices (nwalign_gpu9...cu:701-708): converts the
+ * device-resident headers to the reference's tile-major layout so that
+ * the reference's own NwTrace2_Sparse / NwHash2_Sparse / NwPrintScore2_Sparse accept them. */
+NWB200_API int  nwb200_copy_headers(nwb200_ctx* ctx, int32_t* hrow_host, int32_t* hcol_host);
+
+/* Replaces NwHash2_Sparse / NwHash1_Plain (nwtrace2_sparse.cpp:263-340, nwtrace1_plain.cpp:133-154):
+ * the djb2-xor fold over every cell of the score matrix.  The fold is inherently sequential;
+ * rows are recomputed on the GPU in slabs from the device-resident sequences and folded on
+ * the host as they stream back. */
+NWB200_API int  nwb200_score_hash(nwb200_ctx* ctx, uint32_t* score_hash);
+
+/* Batch of independent pairs (BASELINE config 3): byte letters in one pool, per-pair
+ * offsets/lengths.  scores[n_pairs] always; if edits != NULL each pair's transcript is written
+ * at edits + edit_off[p] (edit_off[n_pairs] entries in, lengths in edit_len[p] out) and its
+ * trace hash into trace_hashes[p]. */
+NWB200_API int  nwb200_align_batch(nwb200_ctx* ctx, const uint8_t* letters, size_t n_letters,
+                                   const uint64_t* offY, const uint32_t* lenY,
+                                   const uint64_t* offX, const uint32_t* lenX, size_t n_pairs,
+                                   int32_t* scores, char* edits /* nullable */, const uint64_t* edit_off,
+                                   uint32_t* edit_len, uint32_t* trace_hashes);
+/* Split form: upload once, run on the stream, fetch. */
+NWB200_API int  nwb200_upload_batch(nwb200_ctx* ctx, const uint8_t* letters, size_t n_letters,
+                                    const uint64_t* offY, const uint32_t* lenY,
+                                    const uint64_t* offX, const uint32_t* lenX, size_t n_pairs);
+NWB200_API int  nwb200_batch_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
+NWB200_API int  nwb200_fetch_batch_scores(nwb200_ctx* ctx, int32_t* scores); /* syncs */
+
+/* Introspection. */
+NWB200_API int         nwb200_last_cuda_error(const nwb200_ctx* ctx);
+NWB200_API const char* nwb200_last_error(const nwb200_ctx* ctx);
+NWB200_API int         nwb200_get_timing(const nwb200_ctx* ctx, nwb200_timing* out);
+NWB200_API void*       nwb200_stream(const nwb200_ctx* ctx);                 /* cudaStream_t */
+NWB200_API int         nwb200_sync(nwb200_ctx* ctx);
+NWB200_API int         nwb200_kernel_launches(const nwb200_ctx* ctx);        /* kernels launched so far */
+NWB200_API const char* nwb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NWB200_H */
