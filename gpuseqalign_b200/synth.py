@@ -1,0 +1,87 @@
+"""Deterministic synthetic inputs of SURVEY.md 8(d): splitmix64 residues, mutated copies.
+
+Input generation only (host side, numpy); nothing here aligns anything.
+    state += 0x9E3779B97F4A7C15; z = state
+    z = (z ^ z >> 30) * 0xBF58476D1CE4E5B9;  z = (z ^ z >> 27) * 0x94D049BB133111EB;  out = z ^ z >> 31
+    residue = (out >> 33) % 20      -> letter index 0..19 = ARNDCQEGHILKMFPSTWYV (subst.json:5-24)
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_G = np.uint64(0x9E3779B97F4A7C15)
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+
+
+def splitmix64(seed: int, n: int, start: int = 0) -> np.ndarray:
+    """outputs start .. start+n-1 of the splitmix64 stream whose state was initialised to `seed`."""
+    with np.errstate(over="ignore"):
+        k = np.arange(start + 1, start + n + 1, dtype=np.uint64)
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + k * _G
+        z = (z ^ (z >> np.uint64(30))) * _M1
+        z = (z ^ (z >> np.uint64(27))) * _M2
+        return z ^ (z >> np.uint64(31))
+
+
+def letters(seed: int, n: int) -> np.ndarray:
+    """n residues (uint8, 0..19)."""
+    return ((splitmix64(seed, n) >> np.uint64(33)) % np.uint64(20)).astype(np.uint8)
+
+
+def mutated_copy(x: np.ndarray, seed: int, target_len: int) -> np.ndarray:
+    """SURVEY.md 8(d) 'mutated copy': per residue u = next() % 1000: u < 25 deletion, u < 50 insertion
+    (random residue, then the original), u < 150 substitution, else copy; truncate / pad to target_len."""
+    out = []
+    s = seed & 0xFFFFFFFFFFFFFFFF
+    pos = 0
+
+    def nxt():
+        nonlocal pos
+        v = int(splitmix64(s, 1, pos)[0])
+        pos += 1
+        return v
+
+    # vectorised draw of the decision stream would change the stream order of the inserted residues,
+    # so this stays a simple loop over blocks of pre-drawn numbers
+    draws = splitmix64(s, 2 * len(x) + 2 * target_len + 16)
+    di = 0
+    for r in x:
+        u = int(draws[di] % np.uint64(1000)); di += 1
+        if u < 25:
+            continue
+        if u < 50:
+            out.append(int((draws[di] >> np.uint64(33)) % np.uint64(20))); di += 1
+            out.append(int(r))
+        elif u < 150:
+            out.append(int((draws[di] >> np.uint64(33)) % np.uint64(20))); di += 1
+        else:
+            out.append(int(r))
+    while len(out) < target_len:
+        out.append(int((draws[di] >> np.uint64(33)) % np.uint64(20))); di += 1
+    return np.array(out[:target_len], dtype=np.uint8)
+
+
+def batch_pairs(first_pair: int, n_pairs: int, len_y: int, len_x: int):
+    """cfg3 batch: pair p has X seed 3e6+2p and Y seed 3e6+2p+1.  Returns (letters, offY, lenY, offX, lenX)
+    with all X sequences first, then all Y sequences, in one byte pool."""
+    pool = np.empty(n_pairs * (len_x + len_y), dtype=np.uint8)
+    # one stream per sequence; vectorised over pairs
+    with np.errstate(over="ignore"):
+        p = np.arange(first_pair, first_pair + n_pairs, dtype=np.uint64)
+        for which, ln, base in ((0, len_x, 0), (1, len_y, n_pairs * len_x)):
+            seeds = np.uint64(3_000_000) + np.uint64(2) * p + np.uint64(which)
+            k = np.arange(1, ln + 1, dtype=np.uint64)
+            chunk = max(1, (1 << 22) // max(ln, 1))
+            for lo in range(0, n_pairs, chunk):
+                hi = min(n_pairs, lo + chunk)
+                z = seeds[lo:hi, None] + k[None, :] * _G
+                z = (z ^ (z >> np.uint64(30))) * _M1
+                z = (z ^ (z >> np.uint64(27))) * _M2
+                z = z ^ (z >> np.uint64(31))
+                pool[base + lo * ln: base + hi * ln] = ((z >> np.uint64(33)) % np.uint64(20)).astype(np.uint8).ravel()
+    offX = (np.arange(n_pairs, dtype=np.uint64) * np.uint64(len_x))
+    offY = np.uint64(n_pairs * len_x) + np.arange(n_pairs, dtype=np.uint64) * np.uint64(len_y)
+    lenX = np.full(n_pairs, len_x, dtype=np.uint32)
+    lenY = np.full(n_pairs, len_y, dtype=np.uint32)
+    return pool, offY, lenY, offX, lenX
