@@ -1,5 +1,82 @@
-// nw_batch.cuh -- many short independent pairs (BASELINE config 3).
+// nw_batch.cuh -- many independent short pairs (BASELINE config 3): one warp aligns one pair.
+//
+// The reference has no batch path: benchmark.cpp:406 calls align once per pair, and gpu9 launches
+// trows+tcols-1 kernels of <= min(trows,tcols) blocks for each (3 launches of <= 2 blocks for 256 x 256).
+// Here a pair of up to 32*R rows is ONE band: a warp sweeps it with the lanes one column apart (K = 1, the
+// fill / drain of the systolic array costs 31 of m+31 steps), nothing touches HBM but the letters (read
+// once) and the 4-byte score.  Warps take pairs from an atomic ticket, so ragged batches balance themselves.
 #pragma once
-#include "nw_common.cuh"
+#include "nw_sweep.cuh"
+
 namespace nwb {
+
+struct BatchArgs {
+    const uint8_t* letters;              // one byte pool
+    const unsigned long long* offY;      // per pair: offset / length of the row sequence ...
+    const unsigned* lenY;
+    const unsigned long long* offX;      // ... and of the column sequence
+    const unsigned* lenX;
+    unsigned long long npairs;
+    const uint8_t* sprime;
+    int S;
+    int gap;
+    int* scores;                         // H[lenY][lenX] per pair; kBatchTooTall if lenY > 32*R (the host re-runs those as single pairs)
+    unsigned long long* ticket;
+};
+
+constexpr int kBatchTooTall = (int)0x80000000;
+
+template <int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
+{
+    constexpr int K = 1;
+    using SC = Sched<R, K>;
+    constexpr int By = SC::By, PD = SC::PD, XR = SC::XR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
+    const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
+    ChunkIO io;
+    io.prof_lane = sm.prof + lane * 4 * SC::WPL;
+    io.rin_chunk = nullptr; io.rin_next = nullptr; io.hr_out = nullptr; io.tag = 0; io.map_out = nullptr; io.org0 = 0;
+    io.dirs_lane = nullptr; io.negg = 0;
+
+    for (;;) {
+        unsigned long long p = 0;
+        if (lane == 0) p = atomicAdd(a.ticket, 1ull);
+        p = __shfl_sync(kFull, p, 0);
+        if (p >= a.npairs) break;
+        const int n = (int)a.lenY[p], m = (int)a.lenX[p];
+        if (n == 0 || m == 0) { if (lane == 0) a.scores[p] = (n + m) * a.gap; continue; }
+        if (n > By) { if (lane == 0) a.scores[p] = kBatchTooTall; continue; }
+        const uint8_t* y = a.letters + a.offY[p];
+        const uint8_t* x = a.letters + a.offX[p];
+        const int pad = By - n;                                    // rows are aligned to the bottom of the band
+        __syncwarp();
+        build_profile<R, K>(sm, a.sprime, a.S, y, (long long)lane * R - pad, n, lane, nullptr);
+        for (int c = -32 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
+        for (int g = 0; g < PD; g++) {
+            const int c = 32 * g + lane;
+            sm.put_letter(c, c < m ? (unsigned)__ldg(x + c) * SC::LSTRIDE : ZOFF);
+        }
+        __syncwarp();
+        Lane<R, 0> st;
+#pragma unroll
+        for (int r = 0; r < R; r++) st.h[r] = 0;
+        st.dprev = 0; st.up_next = 0; st.oprev = 0; st.oup_next = 0; st.o[0] = 0;
+        const int nlc = SC::nlc(m);
+        for (int lc = 0; lc < nlc; lc++) {
+            const int cp = 32 * (lc + PD) + lane;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) * SC::LSTRIDE : ZOFF;
+            io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
+            sweep_chunk<R, K, 0, false>(st, lane, io, nullptr);
+            __syncwarp();
+            sm.put_letter(cp, pf_x);
+            __syncwarp();
+        }
+        // lane 31's last row is row n of the matrix, frozen at column m: un-shift H = P + (n+m)*gap
+        if (lane == 31) a.scores[p] = st.h[R - 1] + (n + m) * a.gap;
+    }
+}
+
 }  // namespace nwb

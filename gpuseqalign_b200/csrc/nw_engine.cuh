@@ -47,12 +47,14 @@ struct PinBuf {
 
 struct Geometry {
     int R = 4, W = 4, K = 2;
-    int By = 512, Bx = 512;
+    int By = 128, Bx = 512;          // band height (32*R), snapshot spacing in columns
     int n = 0, m = 0;
-    int trows = 0, tcols = 0;
-    int nlc = 0;
-    long long ldr = 0, ldc = 0;
-    long long npad = 0;
+    int nb = 0, pad = 0;             // bands, padding rows above row 1 (rows are aligned to the bottom)
+    int tcols = 0;
+    int nlc = 0;                     // 32-step chunks per band
+    int snap_chunks = 16, nsnap = 0;
+    long long ldr = 0;               // header-row pitch in elements
+    long long npad = 0;              // nb * By
 };
 
 }  // namespace nwb
@@ -74,20 +76,23 @@ struct nwb200_ctx {
     bool pair_resident = false;
     bool headers_valid = false;
     bool fill_done = false;
-    nwb::DevBuf d_y, d_x, d_HR, d_HC, d_lastcol, d_sync, d_score;
-    nwb::PinBuf h_stage, h_small;
+    nwb::DevBuf d_y, d_x, d_HR, d_snap, d_lastcol, d_sync;
+    nwb::PinBuf h_stage, h_small, h_trace;
     // traceback
-    nwb::DevBuf d_exit, d_path, d_ops, d_edit, d_tmeta;
+    nwb::DevBuf d_map, d_tmeta, d_ops, d_dense, d_export;
     bool trace_done = false;
+    bool edit_cached = false;
+    std::string last_edit;
+    unsigned last_hash = 0;
     // batch
-    nwb::DevBuf d_bletters, d_boffY, d_boffX, d_blenY, d_blenX, d_bscores, d_bsync;
-    size_t batch_pairs = 0;
+    nwb::DevBuf d_bletters, d_bmeta, d_bscores;
+    size_t batch_pairs = 0, batch_letters = 0;
+    int batch_maxy = 0;
     bool batch_resident = false;
+    nwb::PinBuf h_batch;
     // bookkeeping
     nwb200_timing timing = {};
     unsigned epoch = 0;
-    bool debug_stamps = false;
-    unsigned backoff_ns = 1500;
     int launches = 0;
     cudaError_t last_cuda = cudaSuccess;
     std::string last_error;

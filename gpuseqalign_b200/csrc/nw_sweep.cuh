@@ -1,0 +1,223 @@
+// nw_sweep.cuh -- the band sweep: the one device routine every kernel of the engine is built on.
+//
+// It replaces the tile computation of the reference (Nw_Gpu9_KernelB, nwalign_gpu9_mlsp_diagdiagdiag.cu:69-360,
+// recurrence at :292-294) and its host-side twin used by the traceback (NwTrace2_AlignTile,
+// nwtrace2_sparse.cpp:40-96).  B200-first design, not a translation:
+//
+//   * The matrix is cut into horizontal BANDS of By = 32*R rows.  One WARP sweeps one band left to right
+//     over all columns in a single pass: lane l owns rows l*R .. l*R+R-1 of the band and is at column
+//     c = s - K*l at step s, so the warp is a 32-stage systolic array whose lanes are K columns apart.
+//     All state lives in registers (R "left" values + one diagonal value per lane); the value crossing a lane
+//     boundary moves with ONE rotate-shuffle per step (K = 2: issued one step early, off the critical path).
+//   * Arithmetic is done in shifted coordinates P[i][j] = H[i][j] - (i+j)*gap (the
+//     reference's half-way form is nwalign_gpu1_ml_diag.cu:65-70):
+//         P[i][j] = max3(P[i-1][j-1] + s', P[i-1][j], P[i][j-1]),   s' = max(subst - 2*gap, 0)  (a byte)
+//     One cell = one IDP.4A (adds byte r of a packed per-lane profile word to the diagonal value) + one
+//     VIMNMX3 (DPX 3-way max): two issue slots on two pipes.  Row 0 and column 0 of P are all zero, so
+//     there is no header-init kernel (reference Nw_Gpu9_KernelA).  P is monotone along rows and columns;
+//     therefore a column whose profile row is all zero (columns outside the sequence) FREEZES every row at
+//     its last value and a row whose profile bytes are zero fed with zeros stays zero: padding needs no
+//     bounds checks anywhere in the inner loop.  Rows are aligned to the BOTTOM of the matrix (the padding
+//     rows sit above row 1 of band 0), so the last band's bottom row is row n and the score is the last
+//     value lane 31 holds.
+//   * MODE selects what a cell leaves behind:
+//       0  score       nothing (the band's bottom row streams out as the next band's top row)
+//       1  origin      every cell carries the column at which its traceback path leaves the band through the
+//                      top row; the bottom row's labels form the band's entry->exit map
+//       2  directions  a 2-bit move code per cell (0 '=', 1 'X', 2 'I' up, 3 'D' left) written to shared
+//                      memory for the walker.  The choice follows nwtrace1_plain.cpp:29-100 /
+//                      nwtrace2_sparse.cpp:149-180 exactly: compare the NEIGHBOUR SCORES diag, up, left with
+//                      strict '<', preference diag > up > left.  In shifted coordinates H_diag vs H_up vs
+//                      H_left is (P_diag - gap) vs P_up vs P_left.
+#pragma once
+#include "nw_common.cuh"
+
+namespace nwb {
+
+constexpr int kPadL = 64;     // elements of padding in front of every header row (columns -64..-1 are scratch)
+
+template <int R, int K>
+struct Sched {
+    static_assert(R == 4 || R == 8 || R == 16, "rows per lane");
+    static_assert(K == 1 || K == 2, "lane skew");
+    static constexpr int WPL = R / 4;                  // profile words per lane and letter
+    static constexpr int By = 32 * R;                  // rows per band
+    static constexpr int LAG = 31 * K;                 // columns lane 31 is behind lane 0
+    static constexpr int PD = 2;                       // top-row / letter groups prefetched ahead
+    static constexpr int VR = 128;                     // ints in the top-row ring (4 groups of 32 columns)
+    static constexpr int XR = 256;                     // entries in the letter ring (8 groups)
+    static constexpr int XM = 32;                      // mirror entries behind the letter ring
+    static constexpr int LSTRIDE = 128 * WPL;          // bytes between the profile rows of two letters
+    static constexpr int SNAP_INTS = R + 4;            // per-lane snapshot: h[R], dprev, up_next, 2 pad
+    static_assert(kPadL >= LAG + 1, "header row padding");
+    __host__ __device__ static constexpr int nlc(int m) { return (m + LAG + 31) / 32; }      // 32-step chunks per band
+    __host__ __device__ static constexpr size_t prof_bytes(int S) { return (size_t)(S + 1) * LSTRIDE; }
+    __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
+    {
+        return (prof_bytes(S) + (size_t)VR * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
+    }
+};
+
+// Register state of one lane.
+template <int R, int MODE>
+struct Lane {
+    int h[R];        // h[r] = P[row r][c-1]: the left neighbour of the cell row r computes next
+    int dprev;       // P[row0-1][c-1]: the diagonal neighbour of row 0 (= the previous step's `up`)
+    int up_next;     // K == 2: the shuffled upper neighbour for the next step
+    int o[MODE == 1 ? R : 1];   // MODE 1: origin labels travelling with h / dprev / up_next
+    int oprev;
+    int oup_next;
+};
+
+// Warp-private shared memory.
+template <int R, int K>
+struct WarpSmem {
+    using SC = Sched<R, K>;
+    unsigned char* prof;     // [(S+1)][32 lanes][WPL] words: bytes s'(y[row r], letter)
+    int* rin;                // [VR] top-row ring: P[top][c] at (c & (VR-1))
+    unsigned short* xs;      // [XR + XM] letter ring: profile byte offset (letter * LSTRIDE) of column c at (c & (XR-1))
+    __device__ __forceinline__ WarpSmem(unsigned char* base, int S)
+    {
+        prof = base;
+        rin = reinterpret_cast<int*>(base + SC::prof_bytes(S));
+        xs = reinterpret_cast<unsigned short*>(rin + SC::VR);
+    }
+    __device__ __forceinline__ void put_letter(int c, unsigned off16)
+    {
+        const int p = c & (SC::XR - 1);
+        xs[p] = (unsigned short)off16;
+        if (p < SC::XM) xs[p + SC::XR] = (unsigned short)off16;
+    }
+};
+
+// Per-lane packed profile for the band's rows; row S is the all-zero row used outside the sequence.
+// yrow0 = 0-based index into y of this lane's first row (negative / >= n: padding row, zero bytes).
+template <int R, int K>
+__device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const uint8_t* __restrict__ sprime, int S,
+                                              const uint8_t* __restrict__ y, long long yrow0, long long n, int lane, unsigned* yl_out)
+{
+    using SC = Sched<R, K>;
+    constexpr int WPL = SC::WPL;
+    unsigned yl[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const long long i = yrow0 + r;
+        yl[r] = (i >= 0 && i < n) ? (unsigned)__ldg(y + i) : 0xffu;
+        if (yl_out) yl_out[r] = yl[r];
+    }
+    unsigned* pl = reinterpret_cast<unsigned*>(sm.prof) + lane * WPL;
+    for (int xl = 0; xl < S; xl++) {
+#pragma unroll
+        for (int q = 0; q < WPL; q++) {
+            unsigned word = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const unsigned yy = yl[q * 4 + r];
+                const unsigned b = (yy != 0xffu) ? (unsigned)__ldg(sprime + yy * S + xl) : 0u;
+                word |= b << (8 * r);
+            }
+            pl[(size_t)xl * 32 * WPL + q] = word;
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < WPL; q++) pl[(size_t)S * 32 * WPL + q] = 0u;
+}
+
+// What one chunk reads and writes besides the lane state.
+struct ChunkIO {
+    const unsigned short* xs_lane;   // &xs[(32*lc - K*lane) & (XR-1)]: this lane's letter offsets, index s
+    const unsigned char* prof_lane;  // &prof[0][lane][0] as bytes
+    const int* rin_chunk;            // &rin[(32*lc) & (VR-1)]: top row for lane 0, index s
+    const int* rin_next;             // &rin[(32*lc + 32) & (VR-1)]: first element of the next group (K == 2 look-ahead)
+    unsigned long long* hr_out;      // MODE 0: &HR_out[32*lc - LAG] (lane 31 stores element s), nullptr = keep nothing
+    unsigned tag;                    // MODE 0: epoch tag of the tagged header elements
+    int* map_out;                    // MODE 1: &map[32*lc - LAG] (lane 31 stores element s)
+    int org0;                        // MODE 1: label of the cell above lane 0 at step 0 of this chunk (= 32*lc + 1)
+    unsigned char* dirs_lane;        // MODE 2: &dirs[(32*(lc-lc0))*32 + lane], one byte (R=4) / two (R=8) / four (R=16) per step
+    int negg;                        // -gap
+};
+
+// One 32-step chunk of one warp.
+template <int R, int K, int MODE, bool TOP = true>
+__device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, const ChunkIO& io, const unsigned* __restrict__ yoff)
+{
+    using SC = Sched<R, K>;
+    constexpr int WPL = SC::WPL;
+    const int src_lane = (lane + 31) & 31;
+    const bool last = (lane == 31);
+    // software pipeline: letter offsets 3 steps ahead, profile words 2 steps ahead, top row 2 steps ahead
+    unsigned xo[32 + 3];
+    unsigned pw[32 + 2][WPL];
+    int rv[32 + 2];
+    auto load_pw = [&](int s) {
+        const unsigned char* pp = io.prof_lane + xo[s];
+        if constexpr (WPL == 1) pw[s][0] = *reinterpret_cast<const unsigned*>(pp);
+        else if constexpr (WPL == 2) { uint2 v = *reinterpret_cast<const uint2*>(pp); pw[s][0] = v.x; pw[s][1] = v.y; }
+        else { uint4 v = *reinterpret_cast<const uint4*>(pp); pw[s][0] = v.x; pw[s][1] = v.y; pw[s][2] = v.z; pw[s][3] = v.w; }
+    };
+    auto load_rv = [&](int s) {      // rv[s] = top-row value handed to lane 0 by the shuffle issued at step s
+        constexpr int A = (K == 2) ? 1 : 0;
+        if constexpr (TOP) rv[s] = (s + A < 32) ? io.rin_chunk[s + A] : io.rin_next[0];
+        else rv[s] = 0;                                   // row 0 of P above the band: no top-row ring at all
+    };
+#pragma unroll
+    for (int s = 0; s < 3; s++) xo[s] = io.xs_lane[s];
+#pragma unroll
+    for (int s = 0; s < 2; s++) { load_pw(s); load_rv(s); }
+#pragma unroll
+    for (int s = 0; s < 32; s++) {
+        if (s + 3 < 32) xo[s + 3] = io.xs_lane[s + 3];
+        if (s + 2 < 32) { load_pw(s + 2); load_rv(s + 2); }
+        // Rotate-shuffle: lanes 0..30 hand their bottom row to the lane below; lane 31 hands lane 0 its next
+        // input from the row above the band, so the result feeds the first VIMNMX3 directly.
+        int up, oup = 0;
+        if constexpr (K == 1) {
+            up = __shfl_sync(kFull, last ? rv[s] : st.h[R - 1], src_lane);
+            if constexpr (MODE == 1) oup = __shfl_sync(kFull, last ? io.org0 + s : st.o[R - 1], src_lane);
+        } else {
+            up = st.up_next;
+            st.up_next = __shfl_sync(kFull, last ? rv[s] : st.h[R - 1], src_lane);     // consumed at step s+1
+            if constexpr (MODE == 1) {
+                oup = st.oup_next;
+                st.oup_next = __shfl_sync(kFull, last ? io.org0 + s + 1 : st.o[R - 1], src_lane);
+            }
+        }
+        int diag = st.dprev, odiag = st.oprev;
+        st.dprev = up;
+        if constexpr (MODE == 1) st.oprev = oup;
+        unsigned codes = 0;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int left = st.h[r];
+            const int t = add_byte(pw[s][r >> 2], 1u << (8 * (r & 3)), diag);
+            const int nv = max3(t, up, left);
+            if constexpr (MODE != 0) {
+                const int cd = diag + io.negg;            // H_diag - H_up/H_left offset: P_diag - gap
+                const bool p1 = cd < up;                  // nwtrace1_plain.cpp:57: max < up  -> move up
+                const int b1 = max(cd, up);
+                const bool p2 = b1 < left;                // nwtrace1_plain.cpp:65: max < left -> move left
+                if constexpr (MODE == 1) {
+                    const int oleft = st.o[r];
+                    const int on = p2 ? oleft : (p1 ? oup : odiag);
+                    odiag = oleft; oup = on; st.o[r] = on;
+                } else {
+                    const unsigned eqx = (xo[s] == yoff[r]) ? 0u : 1u;
+                    const unsigned code = p2 ? 3u : (p1 ? 2u : eqx);
+                    codes |= code << (2 * r);
+                }
+            }
+            diag = left; up = nv; st.h[r] = nv;
+        }
+        if constexpr (MODE == 0) {
+            if (io.hr_out != nullptr && last) st_relaxed64(io.hr_out + s, pack_tagged(st.h[R - 1], io.tag));
+        } else if constexpr (MODE == 1) {
+            if (last) io.map_out[s] = st.o[R - 1];
+        } else {
+            if constexpr (R == 4) io.dirs_lane[s * 32] = (unsigned char)codes;
+            else if constexpr (R == 8) reinterpret_cast<unsigned short*>(io.dirs_lane)[s * 32] = (unsigned short)codes;
+            else reinterpret_cast<unsigned*>(io.dirs_lane)[s * 32] = codes;
+        }
+    }
+}
+
+}  // namespace nwb

@@ -1,48 +1,281 @@
-// nw_trace.cuh -- traceback on the GPU from the sparse tile headers (the reference's
-// nwtrace2_sparse scheme, nwtrace2_sparse.cpp:102-257, re-designed for the device) and the
-// export of the device-resident headers in the reference's own layout.
+// nw_trace.cuh -- traceback on the GPU from the sparse representation the fill leaves in HBM (band header
+// rows + register snapshots): the reference's nwtrace2_sparse scheme (NwTrace2_Sparse,
+// nwtrace2_sparse.cpp:102-257: recompute a tile from its headers, walk it, hop to the next tile), re-designed
+// so that nothing but a short pointer chase is sequential:
+//
+//   pass A  nw_map_kernel    every band, in parallel, at full issue rate: re-sweep the band from its header row
+//                            with an ORIGIN label per cell (the column at which the traceback path through that
+//                            cell leaves the band through its top row).  The bottom row's labels are the band's
+//                            entry -> exit map.
+//   pass B  nw_hop_kernel    one thread: entry[nb-1] = m, entry[b-1] = map[b][entry[b]] -- nb dependent loads.
+//                            Now every band knows where the path enters it.
+//   pass C  nw_walk_kernel   every band, in parallel: resume the sweep from the nearest snapshot left of the entry,
+//                            write 2-bit move codes for the window into shared memory, walk them (the only
+//                            cell-by-cell sequential part, <= By + window steps per band), emit one byte per move.
+//   pass D  nw_pack_kernel   concatenate the per-band move lists (backward path order) into one dense array.
+//
+// The move choice is the reference's (nwtrace1_plain.cpp:29-100): neighbour scores, strict '<', diag > up > left.
+// Run-length encoding + djb2 hash of the transcript (nwtrace1_plain.cpp:81-128) is O(path) byte work done by the
+// host on the dense move list.
 #pragma once
-#include "nw_common.cuh"
+#include "nw_sweep.cuh"
 
 namespace nwb {
 
-// Device headers (P-space, plain row-major) -> reference layout (H-space, tile-major;
-// SURVEY.md App. A-4, producer nwalign_gpu9_mlsp_diagdiagdiag.cu:321-359, consumer
-// nwtrace2_sparse.cpp:48-67):
-//   hrow[(iT*tcols + jT)*(1+Bx) + k] = H[iT*By][jT*Bx + k]
-//   hcol[(iT*tcols + jT)*(1+By) + k] = H[iT*By + k][jT*Bx]
-// with H[i][j] = P[i][j] + (i+j)*gap, P[0][*] = P[*][0] = 0,
-// HR[b*ldr + c] = (tag << 32 | P[b*By][c+1]) (b >= 1), HC[q*ldc + i0] = P[i0+1][(q+1)*Bx].
-// Entries that lie outside the real matrix (padding) are written as 0; nothing consumes them.
-__global__ void nw_export_headers_kernel(const unsigned long long* __restrict__ HR, long long ldr, const int* __restrict__ HC, long long ldc,
-                                         int n, int m, int By, int Bx, int trows, int tcols, int gap,
-                                         int* __restrict__ hrow, int* __restrict__ hcol)
+struct TraceArgs {
+    const uint8_t* y;
+    const uint8_t* x;
+    int n, m;
+    const uint8_t* sprime;
+    int S;
+    int negg;                        // -gap
+    const unsigned long long* HR;    // header rows of the fill (low 32 bits = P)
+    long long ldr;
+    const int* snap;                 // snapshots of the fill
+    int nsnap, snap_chunks;
+    int* map;                        // map[b*ldr + kPadL + c]: exit column (matrix j) on the top row for entry (bottom row, column c)
+    int nb, pad;
+    int* entry;                      // [nb]   entry column (matrix j) of the path on the bottom row of band b
+    int* exitj;                      // [nb]   column at which the walker left band b (consistency check)
+    long long* off;                  // [nb+1] start of band b's region in ops (backward path order: band nb-1 first)
+    int* cnt;                        // [nb]   moves emitted by band b
+    unsigned char* ops;              // per-band move lists, codes 0 '=', 1 'X', 2 'I', 3 'D'
+    unsigned char* dense;            // packed backward move list
+    long long* total;                // [2]: total moves, consistency flag
+};
+
+// Loads a plain (already complete) header-row group into the top-row ring.
+template <int R, int K>
+__device__ __forceinline__ void load_top_group(const WarpSmem<R, K>& sm, const unsigned long long* hr_in, int g, int m, int lane)
 {
-    const long long nrow = (long long)trows * tcols * (1 + Bx);
-    const long long ncol = (long long)trows * tcols * (1 + By);
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nrow; e += stride) {
-        long long t = e / (1 + Bx); int k = (int)(e % (1 + Bx));
-        int iT = (int)(t / tcols), jT = (int)(t % tcols);
-        long long i = (long long)iT * By, j = (long long)jT * Bx + k;
-        int v = 0;
-        if (i <= n && j <= m) {
-            int P = (i == 0 || j == 0) ? 0 : (int)(unsigned)HR[(long long)iT * ldr + (j - 1)];
-            v = P + (int)((i + j) * gap);
+    const int c = 32 * g + lane;
+    sm.rin[c & (Sched<R, K>::VR - 1)] = (hr_in != nullptr && c < m) ? (int)(unsigned)__ldg(hr_in + c) : 0;
+}
+template <int R, int K>
+__device__ __forceinline__ void load_letter_group(WarpSmem<R, K>& sm, const uint8_t* __restrict__ x, int g, int m, int lane, unsigned zoff)
+{
+    const int c = 32 * g + lane;
+    sm.put_letter(c, (c >= 0 && c < m) ? (unsigned)__ldg(x + c) * Sched<R, K>::LSTRIDE : zoff);
+}
+
+// ---------------------------------------------------------------------------------------------- pass A
+template <int R, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
+{
+    using SC = Sched<R, K>;
+    constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
+    const int m = a.m, nlc = SC::nlc(m);
+    const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
+    const int nwarps = gridDim.x * WARPS;
+    // band 0 needs no map: the walker of band 0 ends the path itself
+    for (int b = 1 + blockIdx.x * WARPS + w; b < a.nb; b += nwarps) {
+        const long long prow0 = (long long)b * By + (long long)lane * R;
+        build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+        const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
+        for (int g = -2; g < PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
+        for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
+        __syncwarp();
+        for (int g = 0; g < PD; g++) load_top_group<R, K>(sm, hr_in, g, m, lane);
+        __syncwarp();
+        Lane<R, 1> st;
+#pragma unroll
+        for (int r = 0; r < R; r++) { st.h[r] = 0; st.o[r] = 0; }
+        st.dprev = 0; st.oprev = 0;
+        st.up_next = (lane == 0) ? sm.rin[0] : 0;
+        st.oup_next = (lane == 0) ? 1 : 0;
+        ChunkIO io;
+        io.prof_lane = sm.prof + lane * 4 * SC::WPL;
+        io.hr_out = nullptr; io.tag = 0; io.dirs_lane = nullptr; io.negg = a.negg;
+        int* map_row = a.map + (long long)b * a.ldr + kPadL;
+        for (int lc = 0; lc < nlc; lc++) {
+            const int cp = 32 * (lc + PD) + lane;
+            const int pf_top = (cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
+            io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
+            io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
+            io.map_out = map_row + (32 * lc - LAG);
+            io.org0 = 32 * lc + 1;
+            sweep_chunk<R, K, 1>(st, lane, io, nullptr);
+            __syncwarp();
+            sm.rin[cp & (VR - 1)] = pf_top;
+            sm.put_letter(cp, pf_x);
+            __syncwarp();
         }
-        hrow[e] = v;
     }
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < ncol; e += stride) {
-        long long t = e / (1 + By); int k = (int)(e % (1 + By));
-        int iT = (int)(t / tcols), jT = (int)(t % tcols);
-        long long i = (long long)iT * By + k, j = (long long)jT * Bx;
-        int v = 0;
-        if (i <= n && j <= m) {
-            int P = (i == 0 || j == 0) ? 0 : HC[(long long)(jT - 1) * ldc + (i - 1)];
-            v = P + (int)((i + j) * gap);
+}
+
+// ---------------------------------------------------------------------------------------------- pass B
+// One thread.  Also lays out the per-band regions of the move buffer: band b can emit at most
+// By + (entry[b] - entry[b-1]) moves (+ slack), band 0 at most By + entry[0].
+__global__ void nw_hop_kernel(const TraceArgs a, int By)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int j = a.m;
+    long long off = 0;
+    for (int b = a.nb - 1; b >= 0; b--) {
+        a.entry[b] = j;
+        int jn = 0;
+        if (b > 0 && j > 0) jn = a.map[(long long)b * a.ldr + kPadL + (j - 1)];
+        a.off[b] = off;
+        off += (long long)By + (j - jn) + 4;
+        j = jn;
+    }
+    a.off[a.nb] = off;
+}
+
+// ---------------------------------------------------------------------------------------------- pass C
+template <int R, int K>
+__global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const int minw_chunks, const int seg_chunks)
+{
+    using SC = Sched<R, K>;
+    constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
+    constexpr int DB = R / 4;                                  // bytes of move codes per lane and step
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x;
+    WarpSmem<R, K> sm(smem_raw, a.S);
+    unsigned char* dirs = smem_raw + SC::warp_smem_bytes(a.S);
+    const int m = a.m;
+    const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
+    const long long prow0 = (long long)b * By + (long long)lane * R;
+    unsigned yl[R], yoff[R];
+    build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, yl);
+#pragma unroll
+    for (int r = 0; r < R; r++) yoff[r] = yl[r] * SC::LSTRIDE;
+    const unsigned long long* hr_in = (b > 0) ? a.HR + (long long)b * a.ldr + kPadL : nullptr;
+    const int rmin = (b == 0) ? a.pad : 0;        // first real row of the band (band 0 starts with the padding rows)
+    unsigned char* out = a.ops + a.off[b];
+    int j = a.entry[b];
+    int row = By - 1;
+    int cnt = 0;
+
+    for (;;) {
+        if (j == 0) {                             // column 0: the path goes straight up (nwtrace1_plain.cpp:57-63 with j == 0)
+            const int k = row - rmin + 1;
+            for (int t = lane; t < k; t += 32) out[cnt + t] = 2;
+            cnt += k > 0 ? k : 0;
+            break;
         }
-        hcol[e] = v;
+        if (row < rmin) {                         // left the band through its top row
+            if (b == 0) {                         // matrix row 0: the rest of the path runs left along it
+                for (int t = lane; t < j; t += 32) out[cnt + t] = 3;
+                cnt += j;
+                j = 0;
+            }
+            break;
+        }
+        // ---- recompute the window [32*lc0 .. j-1] of the band with move codes
+        const int lc_hi = ((j - 1) + LAG) / 32;
+        int lc0 = 0;
+        if (lc_hi - minw_chunks >= a.snap_chunks) {
+            int k = (lc_hi - minw_chunks) / a.snap_chunks;
+            if (k > a.nsnap) k = a.nsnap;
+            lc0 = k * a.snap_chunks;
+        }
+        if (lc_hi - lc0 + 1 > seg_chunks) lc0 = lc_hi - seg_chunks + 1;    // cannot happen with valid snapshots; keeps smem in bounds
+        Lane<R, 2> st;
+        st.oprev = 0; st.oup_next = 0; st.o[0] = 0;
+        __syncwarp();
+        for (int g = lc0 - 2; g < lc0 + PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
+        for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
+        __syncwarp();
+        for (int g = lc0; g < lc0 + PD; g++) load_top_group<R, K>(sm, hr_in, g, m, lane);
+        __syncwarp();
+        if (lc0 > 0) {
+            const int* sp = a.snap + (((long long)b * a.nsnap + (lc0 / a.snap_chunks - 1)) * 32 + lane) * SC::SNAP_INTS;
+#pragma unroll
+            for (int r = 0; r < R; r++) st.h[r] = sp[r];
+            st.dprev = sp[R];
+            st.up_next = sp[R + 1];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) st.h[r] = 0;
+            st.dprev = 0;
+            st.up_next = (lane == 0) ? sm.rin[0] : 0;
+        }
+        ChunkIO io;
+        io.prof_lane = sm.prof + lane * 4 * SC::WPL;
+        io.hr_out = nullptr; io.tag = 0; io.map_out = nullptr; io.org0 = 0; io.negg = a.negg;
+        for (int lc = lc0; lc <= lc_hi; lc++) {
+            const int cp = 32 * (lc + PD) + lane;
+            const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
+            io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
+            io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
+            io.dirs_lane = dirs + ((size_t)(32 * (lc - lc0)) * 32 + lane) * DB;
+            sweep_chunk<R, K, 2>(st, lane, io, yoff);
+            __syncwarp();
+            sm.rin[cp & (VR - 1)] = pf_top;
+            sm.put_letter(cp, pf_x);
+            __syncwarp();
+        }
+        // ---- walk the window (uniform across the warp; lane 0 stores)
+        const int cmin = 32 * lc0;                // columns >= cmin are complete in this window (all columns if lc0 == 0)
+        const int sbase = 32 * lc0;
+        while (j > 0 && row >= rmin && (j - 1) >= cmin) {
+            const int ln = row / R, r = row % R;
+            const int step = (j - 1) + K * ln - sbase;
+            unsigned codes;
+            if constexpr (DB == 1) codes = dirs[step * 32 + ln];
+            else if constexpr (DB == 2) codes = reinterpret_cast<const unsigned short*>(dirs)[step * 32 + ln];
+            else codes = reinterpret_cast<const unsigned*>(dirs)[step * 32 + ln];
+            const unsigned code = (codes >> (2 * r)) & 3u;
+            if (lane == 0) out[cnt] = (unsigned char)code;
+            cnt++;
+            if (code < 2u) { row--; j--; }
+            else if (code == 2u) row--;
+            else j--;
+        }
+        __syncwarp();
     }
+    if (lane == 0) { a.cnt[b] = cnt; a.exitj[b] = j; }
+}
+
+// ---------------------------------------------------------------------------------------------- pass D
+// One CTA: exclusive scan of the per-band counts in backward path order, then a coalesced gather.
+__global__ void __launch_bounds__(1024) nw_pack_kernel(const TraceArgs a)
+{
+    __shared__ long long s_base[1024];
+    __shared__ long long s_carry;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_carry = 0; s_bad = 0; }
+    __syncthreads();
+    for (int k0 = 0; k0 < a.nb; k0 += 1024) {
+        const int k = k0 + tid;                          // k-th band in backward order
+        const int b = a.nb - 1 - k;
+        const long long c = (k < a.nb) ? a.cnt[b] : 0;
+        if (k < a.nb && b > 0 && a.exitj[b] != a.entry[b - 1]) s_bad = 1;     // the walker must agree with the map
+        s_base[tid] = c;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {
+            long long v = (tid >= d) ? s_base[tid - d] : 0;
+            __syncthreads();
+            s_base[tid] += v;
+            __syncthreads();
+        }
+        const long long incl = s_base[tid];
+        __syncthreads();
+        s_base[tid] = s_carry + incl - c;                // exclusive base of band k in the dense list
+        __syncthreads();
+        if (tid == 1023) s_carry += incl;
+        // one warp per band, coalesced
+        const int lane = tid & 31, w = tid >> 5;
+        for (int kk = w; kk < 1024 && k0 + kk < a.nb; kk += 32) {
+            const int bb = a.nb - 1 - (k0 + kk);
+            const unsigned char* src = a.ops + a.off[bb];
+            const long long base = s_base[kk];
+            const int cc = a.cnt[bb];
+            for (int t = lane; t < cc; t += 32) a.dense[base + t] = src[t];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { a.total[0] = s_carry; a.total[1] = s_bad; }
 }
 
 }  // namespace nwb

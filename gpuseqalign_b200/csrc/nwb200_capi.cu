@@ -33,37 +33,40 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime
 int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
 {
     Geometry& g = c->g;
-    int R = 4, W = 4, K = 0, Bx = 512;
+    int R = 0, W = 4, K = 2, Bx = 512;
     if (p) {
         if (p->rows_per_lane) R = p->rows_per_lane;
         if (p->warps_per_block) W = p->warps_per_block;
         if (p->tile_cols) Bx = p->tile_cols;
         if (p->reserved) K = p->reserved;
     }
-    if (!(R == 4 || R == 8) || !(W == 4 || W == 8) || Bx < 32 || (Bx % 32) != 0 || !(K == 0 || K == 1 || K == 2))
-        return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8}, warps_per_block in {4,8}, tile_cols multiple of 32)");
-    const int By = R * 32 * W;
-    const long long trows = ((long long)n + By - 1) / By;
-    if (K == 0) K = (trows <= 4LL * c->sm_count) ? 2 : 1;     // few bands: latency-bound -> shuffle off the critical path
+    if (R == 0) R = ((long long)n <= 4LL * 32 * 4 * c->sm_count) ? 4 : 8;      // one warp per SM sub-partition while that covers all rows
+    if (!(R == 4 || R == 8 || R == 16) || !(W == 1 || W == 2 || W == 4 || W == 8) || Bx < 32 || (Bx % 32) != 0 || Bx > (R == 16 ? 512 : 1024) || !(K == 1 || K == 2))
+        return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8,16}, warps_per_block in {1,2,4,8}, tile_cols multiple of 32 up to 1024, skew in {1,2})");
+    const int By = R * 32;
+    long long nb = ((long long)n + By - 1) / By;
+    if (nb < 1) nb = 1;
     g.R = R; g.W = W; g.K = K; g.By = By; g.Bx = Bx; g.n = n; g.m = m;
-    g.trows = (int)(trows < 1 ? 1 : trows);
+    g.nb = (int)nb;
+    g.pad = (int)(nb * By - n);
     g.tcols = (m + Bx - 1) / Bx; if (g.tcols < 1) g.tcols = 1;
-    g.nlc = (m + (31 * (R + K - 1) + R - 1) + 31) / 32;      // Sched<R,W,K>::nlc(m)
-    g.ldr = 32LL * g.nlc;
-    g.npad = (long long)g.trows * By;
-    g.ldc = g.npad;
+    g.nlc = (m + 31 * K + 31) / 32;                          // Sched<R,K>::nlc(m)
+    g.ldr = ((long long)kPadL + 32LL * g.nlc + 32 + 31) / 32 * 32;
+    g.snap_chunks = Bx / 32;
+    g.nsnap = g.nlc / g.snap_chunks;
+    g.npad = nb * By;
     return NWB200_SUCCESS;
 }
 
-template <int R, int W, int K>
+template <int R, int K, int W>
 int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
 {
-    size_t smem = Sched<R, W, K>::smem_bytes(c->S);
+    size_t smem = Sched<R, K>::warp_smem_bytes(c->S) * W;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nw_fill_kernel<R, W, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(nw_fill_kernel<R, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(fill)", e);
     }
-    nw_fill_kernel<R, W, K><<<grid, W * 32, smem, c->stream>>>(a);
+    nw_fill_kernel<R, K, W><<<grid, W * 32, smem, c->stream>>>(a);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel launch", e);
@@ -73,13 +76,15 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
 int launch_fill(nwb200_ctx* c, const FillArgs& a)
 {
     const Geometry& g = c->g;
-    int per_sm = 2048 / (g.W * 32);
-    if (per_sm > 8) per_sm = 8;
+    // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
+    // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
+    long long ctas_needed = ((long long)g.nb + g.W - 1) / g.W;
+    int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
-    if (grid > g.trows) grid = g.trows;
-#define NWB_CASE(R_, W_, K_) if (g.R == R_ && g.W == W_ && g.K == K_) return launch_fill_t<R_, W_, K_>(c, a, (int)grid)
-    NWB_CASE(4, 4, 2); NWB_CASE(4, 4, 1); NWB_CASE(8, 4, 1); NWB_CASE(8, 4, 2);
-    NWB_CASE(4, 8, 2); NWB_CASE(4, 8, 1); NWB_CASE(8, 8, 1); NWB_CASE(8, 8, 2);
+    if (grid > ctas_needed) grid = ctas_needed;
+#define NWB_CASE(R_, K_, W_) if (g.R == R_ && g.K == K_ && g.W == W_) return launch_fill_t<R_, K_, W_>(c, a, (int)grid)
+    NWB_CASE(4, 2, 4); NWB_CASE(4, 1, 4); NWB_CASE(8, 2, 4); NWB_CASE(8, 1, 4); NWB_CASE(16, 2, 4); NWB_CASE(16, 1, 4);
+    NWB_CASE(4, 2, 1); NWB_CASE(4, 2, 2); NWB_CASE(4, 2, 8); NWB_CASE(8, 2, 1); NWB_CASE(8, 2, 2); NWB_CASE(8, 2, 8);
 #undef NWB_CASE
     return fail(c, NWB200_ERR_INVALID_VALUE, "no kernel instance for these tile parameters");
 }
@@ -116,11 +121,11 @@ void nwb200_destroy(nwb200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_HC, &c->d_lastcol, &c->d_sync, &c->d_score,
-                      &c->d_exit, &c->d_path, &c->d_ops, &c->d_edit, &c->d_tmeta,
-                      &c->d_bletters, &c->d_boffY, &c->d_boffX, &c->d_blenY, &c->d_blenX, &c->d_bscores, &c->d_bsync})
+    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
+                      &c->d_map, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export,
+                      &c->d_bletters, &c->d_bmeta, &c->d_bscores})
         b->release();
-    c->h_stage.release(); c->h_small.release();
+    c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -164,8 +169,7 @@ static int upload_common(nwb200_ctx* c, const uint8_t* stage_y, long long n, con
 {
     int rc = plan_geometry(c, (int)n, (int)m, p);
     if (rc) return rc;
-    const Geometry& g = c->g;
-    CU(c, c->d_y.ensure((size_t)g.npad + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc y");
+    CU(c, c->d_y.ensure((size_t)n + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc y");
     CU(c, c->d_x.ensure((size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc x");
     CU(c, cudaEventRecord(c->ev[0], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     CU(c, cudaMemcpyAsync(c->d_y.p, stage_y, (size_t)n, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D y");
@@ -220,15 +224,14 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     cudaSetDevice(c->device);
     const Geometry& g = c->g;
     const bool keep = (flags & NWB200_KEEP_HEADERS) != 0;
-    const int ncolh = g.tcols - 1;
     {
         const size_t before = c->d_HR.cap;
-        CU(c, c->d_HR.ensure(sizeof(unsigned long long) * (size_t)(g.trows + 1) * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc header rows");
+        CU(c, c->d_HR.ensure(sizeof(unsigned long long) * (size_t)(g.nb + 1) * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc header rows");
         if (c->d_HR.cap != before)   // fresh memory may hold anything: clear the tag halves once
             CU(c, cudaMemsetAsync(c->d_HR.p, 0, c->d_HR.cap, c->stream), NWB200_ERR_CUDA_GENERAL, "memset header rows");
     }
-    if (keep && ncolh > 0) CU(c, c->d_HC.ensure(sizeof(int) * (size_t)ncolh * (size_t)g.ldc), NWB200_ERR_MEMORY_ALLOCATION, "alloc header columns");
-    CU(c, c->d_lastcol.ensure(sizeof(int) * (size_t)g.npad), NWB200_ERR_MEMORY_ALLOCATION, "alloc last column");
+    const size_t snap_ints = (size_t)g.nb * (size_t)(g.nsnap > 0 ? g.nsnap : 1) * 32 * (size_t)(g.R + 4);
+    if (keep) CU(c, c->d_snap.ensure(sizeof(int) * snap_ints), NWB200_ERR_MEMORY_ALLOCATION, "alloc snapshots");
     CU(c, c->d_sync.ensure(sizeof(int) * 8), NWB200_ERR_MEMORY_ALLOCATION, "alloc ticket");
     CU(c, cudaEventRecord(c->ev[2], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     CU(c, cudaMemsetAsync(c->d_sync.p, 0, sizeof(int) * 8, c->stream), NWB200_ERR_CUDA_GENERAL, "memset ticket");
@@ -236,18 +239,13 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     a.y = c->d_y.as<uint8_t>(); a.x = c->d_x.as<uint8_t>(); a.n = g.n; a.m = g.m;
     a.sprime = c->d_sprime.as<uint8_t>(); a.S = c->S;
     a.HR = c->d_HR.as<unsigned long long>(); a.ldr = g.ldr;
-    a.HC = c->d_HC.as<int>(); a.ldc = g.ldc;
-    a.lastcol = c->d_lastcol.as<int>();
+    a.snap = (keep && g.nsnap > 0) ? c->d_snap.as<int>() : nullptr;
+    a.nsnap = g.nsnap; a.snap_chunks = g.snap_chunks;
+    a.left = nullptr; a.left_flag = nullptr; a.lastcol = nullptr; a.right_flag = nullptr;
     c->epoch++;
     if (c->epoch == 0) c->epoch = 1;
     a.tag = c->epoch; a.ticket = c->d_sync.as<int>();
-    a.Bx = g.Bx; a.trows = g.trows; a.keep_hdr = keep ? 1 : 0;
-    a.backoff_ns = c->backoff_ns;
-    a.dbg = nullptr;
-    if (c->debug_stamps) {
-        CU(c, c->d_tmeta.ensure(sizeof(unsigned long long) * (4 * (size_t)g.trows + 2400)), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
-        a.dbg = c->d_tmeta.as<unsigned long long>();
-    }
+    a.nb = g.nb; a.pad = g.pad;
     int rc = launch_fill(c, a);
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[3], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
@@ -260,14 +258,17 @@ int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
     if (!c || !align_cost || !c->fill_done) return fail(c, NWB200_ERR_INVALID_VALUE, "no fill has been run");
     cudaSetDevice(c->device);
     const Geometry& g = c->g;
-    int* hs = c->h_small.as<int>();
+    unsigned long long* hs = c->h_small.as<unsigned long long>();
+    // the score is the last real element of the bottom row of the last band
+    const unsigned long long* src = c->d_HR.as<unsigned long long>() + (long long)g.nb * g.ldr + kPadL + (g.m - 1);
     CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
-    CU(c, cudaMemcpyAsync(hs, c->d_lastcol.as<int>() + (g.n - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
+    CU(c, cudaMemcpyAsync(hs, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
     CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel execution", e);
+    if ((unsigned)(hs[0] >> 32) != c->epoch) return fail(c, NWB200_ERR_INVALID_RESULT, "the fill did not publish the score element");
     // un-shift: H[n][m] = P[n][m] + (n+m)*gap
-    *align_cost = (int32_t)((long long)hs[0] + ((long long)g.n + g.m) * c->gap);
+    *align_cost = (int32_t)((long long)(int)(unsigned)hs[0] + ((long long)g.n + g.m) * c->gap);
     c->timing.align_cpy_dev = ev_ms(c->ev[0], c->ev[1]);
     c->timing.align_calc = ev_ms(c->ev[2], c->ev[3]);
     c->timing.align_cpy_host = ev_ms(c->ev[4], c->ev[5]);
@@ -278,9 +279,9 @@ static void fill_hdr_info(const nwb200_ctx* c, nwb200_hdr_info* h)
 {
     if (!h) return;
     const Geometry& g = c->g;
-    h->tile_rows = g.By; h->tile_cols = g.Bx; h->trows = g.trows; h->tcols = g.tcols;
-    h->hrow_elems = (int64_t)g.trows * g.tcols * (1 + g.Bx);
-    h->hcol_elems = (int64_t)g.trows * g.tcols * (1 + g.By);
+    h->tile_rows = g.By; h->tile_cols = g.Bx; h->trows = g.nb; h->tcols = g.tcols;
+    h->hrow_elems = (int64_t)g.nb * g.tcols * (1 + g.Bx);
+    h->hcol_elems = (int64_t)g.nb * g.tcols * (1 + g.By);
 }
 
 int nwb200_align_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8_t* x, int64_t m,
@@ -309,54 +310,8 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
     return NWB200_SUCCESS;
 }
 
-int nwb200_copy_headers(nwb200_ctx* c, int32_t* hrow_host, int32_t* hcol_host)
-{
-    if (!c || !hrow_host || !hcol_host) return fail(c, NWB200_ERR_INVALID_VALUE, "null argument");
-    if (!c->headers_valid) return fail(c, NWB200_ERR_INVALID_VALUE, "the last align did not keep headers (NWB200_KEEP_HEADERS)");
-    cudaSetDevice(c->device);
-    const Geometry& g = c->g;
-    const size_t nrow = (size_t)g.trows * g.tcols * (1 + g.Bx), ncol = (size_t)g.trows * g.tcols * (1 + g.By);
-    CU(c, c->d_edit.ensure(sizeof(int) * (nrow + ncol)), NWB200_ERR_MEMORY_ALLOCATION, "alloc header export");
-    int* d_hrow = c->d_edit.as<int>();
-    int* d_hcol = d_hrow + nrow;
-    CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
-    {
-        const int threads = 256;
-        size_t total = nrow > ncol ? nrow : ncol;
-        int grid = (int)((total + threads - 1) / threads);
-        if (grid > c->sm_count * 16) grid = c->sm_count * 16;
-        nw_export_headers_kernel<<<grid, threads, 0, c->stream>>>(c->d_HR.as<unsigned long long>(), g.ldr, c->d_HC.as<int>(), g.ldc,
-                                                                   g.n, g.m, g.By, g.Bx, g.trows, g.tcols, c->gap, d_hrow, d_hcol);
-        c->launches++;
-        CU(c, cudaGetLastError(), NWB200_ERR_KERNEL_FAILURE, "export kernel launch");
-    }
-    CU(c, cudaMemcpyAsync(hrow_host, d_hrow, sizeof(int) * nrow, cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H hrow");
-    CU(c, cudaMemcpyAsync(hcol_host, d_hcol, sizeof(int) * ncol, cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H hcol");
-    CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "header export", e);
-    c->timing.align_cpy_host = ev_ms(c->ev[4], c->ev[5]);
-    return NWB200_SUCCESS;
-}
-
 #include "nwb200_capi_trace.inc"
 #include "nwb200_capi_batch.inc"
-
-// developer aid (not part of the public header): per-band globaltimer stamps of the next fills
-NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, long long enable, unsigned long long* out, int max_bands)
-{
-    if (!c) return NWB200_ERR_INVALID_VALUE;
-    c->debug_stamps = (enable & 1) != 0;
-    if (enable >> 8) c->backoff_ns = (unsigned)(enable >> 8);
-    if (out && c->fill_done && c->d_tmeta.p) {
-        int nb = c->g.trows < max_bands ? c->g.trows : max_bands;
-        cudaStreamSynchronize(c->stream);
-        cudaMemcpy(out, c->d_tmeta.p, sizeof(unsigned long long) * 4 * nb, cudaMemcpyDeviceToHost);
-        if (max_bands >= c->g.trows + 600) cudaMemcpy(out + 4 * (size_t)max_bands, (unsigned long long*)c->d_tmeta.p + 4 * (size_t)c->g.trows, sizeof(unsigned long long) * 2400, cudaMemcpyDeviceToHost);
-        return nb;
-    }
-    return 0;
-}
 
 int nwb200_last_cuda_error(const nwb200_ctx* c) { return c ? (int)c->last_cuda : 0; }
 const char* nwb200_last_error(const nwb200_ctx* c) { return c ? c->last_error.c_str() : "null context"; }

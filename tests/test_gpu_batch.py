@@ -1,0 +1,69 @@
+"""GPU parity tests for the batch path (BASELINE config 3): scores of many short pairs vs the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(scoring):
+    from gpuseqalign_b200 import Engine
+    e = Engine(0)
+    e.set_scoring(scoring["subst"]["blosum62"], -11)
+    yield e
+    e.close()
+
+
+def _ragged(rng, n_pairs, max_y, max_x, alphabet=20):
+    lenY = rng.integers(0, max_y + 1, n_pairs).astype(np.uint32)
+    lenX = rng.integers(0, max_x + 1, n_pairs).astype(np.uint32)
+    lens = np.empty(2 * n_pairs, dtype=np.uint64)
+    lens[0::2] = lenY; lens[1::2] = lenX
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    letters = rng.integers(0, alphabet, int(offs[-1]) + 1).astype(np.uint8)
+    return letters, offs[0:-1:2].copy(), lenY, offs[1::2].copy(), lenX
+
+
+def test_batch_256_synthetic(engine, scoring, oracle):
+    from gpuseqalign_b200 import synth
+    subst = scoring["subst"]["blosum62"]
+    pool, offY, lenY, offX, lenX = synth.batch_pairs(0, 4096, 256, 256)
+    got = engine.align_batch(pool, offY, lenY, offX, lenX)
+    exp = oracle.score_batch(pool, offY, lenY, offX, lenX, subst, -11)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("max_y,max_x", [(128, 300), (256, 256), (512, 100), (700, 700)])
+def test_batch_ragged(engine, scoring, oracle, max_y, max_x):
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(max_y + max_x)
+    letters, offY, lenY, offX, lenX = _ragged(rng, 600, max_y, max_x)
+    got = engine.align_batch(letters, offY, lenY, offX, lenX)
+    exp = oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11)
+    assert np.array_equal(got, exp)
+
+
+def test_batch_with_transcripts(engine, scoring, oracle):
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(3)
+    letters, offY, lenY, offX, lenX = _ragged(rng, 40, 300, 300)
+    scores, edits, hashes = engine.align_batch(letters, offY, lenY, offX, lenX, want_trace=True)
+    for p in range(40):
+        y = letters[int(offY[p]): int(offY[p]) + int(lenY[p])]
+        x = letters[int(offX[p]): int(offX[p]) + int(lenX[p])]
+        if y.size == 0 or x.size == 0:
+            assert scores[p] == -11 * (y.size + x.size)
+            continue
+        exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+        assert (scores[p], edits[p], hashes[p]) == (exp.score, exp.edit, exp.trace_hash), p
+
+
+def test_batch_resident_split_form(engine, scoring, oracle):
+    from gpuseqalign_b200 import synth
+    subst = scoring["subst"]["blosum62"]
+    pool, offY, lenY, offX, lenX = synth.batch_pairs(100, 1000, 256, 256)
+    engine.upload_batch(pool, offY, lenY, offX, lenX)
+    exp = oracle.score_batch(pool, offY, lenY, offX, lenX, subst, -11)
+    for _ in range(3):
+        engine.batch_resident()
+        assert np.array_equal(engine.fetch_batch_scores(), exp)

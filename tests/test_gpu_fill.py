@@ -1,7 +1,6 @@
-"""GPU parity tests for the score-matrix fill: engine (through the C ABI) vs the CPU oracle.
-
-Bit-exact: integer scores and every tile-header value that the traceback consumes.
-"""
+"""GPU parity tests for the single-pair path: engine (through the C ABI) vs the CPU oracle and the golden
+vectors generated from the reference's cpu4 + NwTrace1_Plain.  Bit-exact: integer score, run-length
+transcript, trace hash."""
 import numpy as np
 import pytest
 
@@ -33,66 +32,76 @@ def test_golden_scores_i32_entry(engine, golden):
         assert engine.align_i32(sy, sx, keep_headers=True) == c["score"]
 
 
-def test_golden_headers_feed_reference_style_trace(engine, golden, scoring, oracle):
-    """Headers exported in the reference layout must let the (restated) NwTrace2_Sparse
-    reproduce the golden transcript: validates every consumed header value."""
-    from gpuseqalign_b200 import Params
-    subst = scoring["subst"]["blosum62"]
-    for c in golden["cases"][::3]:
+def test_golden_traces(engine, golden):
+    """All 206 reference cases (pair_debug + pair_generated_1 + substring ranges): score, transcript, hash."""
+    for c in golden["cases"]:
         y, x = case_letters(golden, c)
-        score = engine.align(y, x, keep_headers=True, params=Params(tile_cols=64))
-        assert score == c["score"]
-        hrow, hcol = engine.headers()
-        info = engine.info
-        r = oracle.trace_sparse(hrow, hcol, info.tile_rows, info.tile_cols, y, x, subst, -11)
-        assert r.score == c["score"]
-        assert r.edit == c["edit"], (c["y"], c["x"])
+        assert engine.align(y, x, keep_headers=True) == c["score"], (c["y"], c["x"])
+        edit, th = engine.trace()
+        assert edit == c["edit"], (c["y"], c["x"])
+        assert f"{th:08x}" == c["trace_hash"], (c["y"], c["x"])
 
 
-@pytest.mark.parametrize("R,W,K,Bx", [(4, 4, 2, 512), (4, 4, 1, 512), (8, 4, 1, 256), (8, 4, 2, 96), (4, 8, 2, 32), (8, 8, 1, 1024)])
+VARIANTS = [(4, 4, 2, 512), (4, 4, 1, 512), (8, 4, 2, 256), (8, 4, 1, 96), (16, 4, 2, 32), (16, 4, 1, 512),
+            (4, 1, 2, 64), (4, 2, 2, 1024), (4, 8, 2, 128), (8, 1, 2, 512), (8, 2, 2, 64), (8, 8, 2, 1024)]
+
+
+@pytest.mark.parametrize("R,W,K,Bx", VARIANTS)
 def test_random_shapes_all_kernel_variants(engine, scoring, oracle, R, W, K, Bx):
     from gpuseqalign_b200 import Params
     subst = scoring["subst"]["blosum62"]
     rng = np.random.default_rng(R * 100 + W * 10 + K)
-    By = R * 32 * W
-    shapes = [(1, 1), (1, 40), (5, 3), (31, 33), (By - 1, By + 1), (By, 2 * By), (By + 1, 777), (2 * By + 17, 3 * By + 5), (1500, 4100)]
+    By = R * 32
+    shapes = [(1, 1), (1, 40), (5, 3), (31, 33), (By - 1, By + 1), (By, 2 * By), (By + 1, 777), (2 * By + 17, 3 * By + 5),
+              (1500, 4100), (2100, 130), (3 * By, 1)]
     for n, m in shapes:
         y = rng.integers(0, 20, n).astype(np.uint8)
         x = rng.integers(0, 20, m).astype(np.uint8)
-        exp, hrow_o, hcol_o, _ = oracle.fill_rolling(y, x, subst, -11, By, Bx)
+        exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
         got = engine.align(y, x, keep_headers=True, params=Params(R, W, Bx, K))
-        assert got == exp, (n, m)
-        hrow, hcol = engine.headers()
-        info = engine.info
-        assert (info.tile_rows, info.tile_cols) == (By, Bx)
-        # compare every header entry that lies inside the real matrix
-        trows, tcols = info.trows, info.tcols
-        hr = hrow.reshape(trows, tcols, 1 + Bx); hro = hrow_o.reshape(trows, tcols, 1 + Bx)
-        hc = hcol.reshape(trows, tcols, 1 + By); hco = hcol_o.reshape(trows, tcols, 1 + By)
-        for jT in range(tcols):
-            kmax = min(Bx, m - jT * Bx)
-            assert np.array_equal(hr[:, jT, : kmax + 1], hro[:, jT, : kmax + 1]), (n, m, "hrow", jT)
-        for iT in range(trows):
-            kmax = min(By, n - iT * By)
-            assert np.array_equal(hc[iT, :, : kmax + 1], hco[iT, :, : kmax + 1]), (n, m, "hcol", iT)
+        assert got == exp.score, (n, m)
+        assert (engine.info.tile_rows, engine.info.tile_cols) == (By, Bx)
+        edit, th = engine.trace()
+        assert edit == exp.edit, (n, m)
+        assert th == exp.trace_hash, (n, m)
 
 
 def test_similar_sequences_long(engine, scoring, oracle):
-    """A mutated copy (mostly diagonal path) and an unrelated pair at 5000 x 6000."""
+    """A mutated copy (mostly diagonal path), an unrelated pair, and long gap runs at 5000 x 6000."""
+    from gpuseqalign_b200 import synth
     subst = scoring["subst"]["blosum62"]
-    rng = np.random.default_rng(11)
-    x = rng.integers(0, 20, 6000).astype(np.uint8)
-    y = x[:5000].copy()
-    idx = rng.integers(0, 5000, 500)
-    y[idx] = rng.integers(0, 20, 500)
-    exp, _, _, _ = oracle.fill_rolling(y, x, subst, -11)
-    assert engine.align(y, x, keep_headers=False) == exp
-    y2 = rng.integers(0, 20, 5000).astype(np.uint8)
-    exp2, _, _, _ = oracle.fill_rolling(y2, x, subst, -11)
-    assert engine.align(y2, x, keep_headers=False) == exp2
+    x = synth.letters(11, 6000)
+    y = synth.mutated_copy(x, 12, 5000)
+    y2 = synth.letters(13, 5000)
+    y3 = np.concatenate([x[:1000], x[3000:5500]])          # a 2000-column deletion: one long horizontal run
+    for yy in (y, y2, y3):
+        exp = oracle.align_pair(yy, x, subst, -11, want_hash=False, want_trace=True)
+        assert engine.align(yy, x, keep_headers=True) == exp.score
+        edit, th = engine.trace()
+        assert edit == exp.edit and th == exp.trace_hash
+    # rows longer than columns (the reference always has X the longer one; the engine does not care)
+    exp = oracle.align_pair(x, y2[:700], subst, -11, want_hash=False, want_trace=True)
+    assert engine.align(x, y2[:700], keep_headers=True) == exp.score
+    edit, th = engine.trace()
+    assert edit == exp.edit and th == exp.trace_hash
 
 
-def test_other_scoring(engine, scoring, oracle):
+def test_resident_split_form_repeats(engine, scoring, oracle):
+    """upload once, fill + trace many times (the benchmark's device-resident loop); epochs must not leak."""
+    from gpuseqalign_b200 import synth
+    subst = scoring["subst"]["blosum62"]
+    x = synth.letters(21, 3000); y = synth.letters(22, 2500)
+    exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+    engine.upload_pair(y, x)
+    for _ in range(5):
+        engine.fill_resident(True)
+        engine.trace_resident()
+        assert engine.fetch_score() == exp.score
+        edit, th = engine.fetch_trace()
+        assert edit == exp.edit and th == exp.trace_hash
+
+
+def test_other_scoring(scoring, oracle):
     from gpuseqalign_b200 import Engine
     e = Engine(0)
     try:
@@ -102,8 +111,10 @@ def test_other_scoring(engine, scoring, oracle):
         for name, gap in [("blosum45", -5), ("blosum90", -20), ("blosum50", -1), ("blosum80", 0)]:
             subst = scoring["subst"][name]
             e.set_scoring(subst, gap)
-            exp, _, _, _ = oracle.fill_rolling(y, x, subst, gap)
-            assert e.align(y, x, keep_headers=False) == exp, (name, gap)
+            exp = oracle.align_pair(y, x, subst, gap, want_hash=False, want_trace=True)
+            assert e.align(y, x, keep_headers=True) == exp.score, (name, gap)
+            edit, th = e.trace()
+            assert edit == exp.edit and th == exp.trace_hash, (name, gap)
     finally:
         e.close()
 
@@ -118,3 +129,7 @@ def test_error_behaviour(engine):
     assert ei.value.stat == NwStat.errorInvalidValue
     with pytest.raises(NwB200Error):
         engine.align(np.array([], dtype=np.uint8), np.array([1, 2], dtype=np.uint8))
+    engine.align(np.array([1], dtype=np.uint8), np.array([1, 2], dtype=np.uint8), keep_headers=False)
+    with pytest.raises(NwB200Error) as ei:          # traceback needs the headers of the last fill
+        engine.trace()
+    assert ei.value.stat == NwStat.errorInvalidValue
