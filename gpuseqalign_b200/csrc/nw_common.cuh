@@ -75,6 +75,17 @@ __device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned
     return (int)(unsigned)v;
 }
 
+__device__ __forceinline__ int wait_tagged_count(const unsigned long long* p, unsigned long long first, unsigned tag, unsigned& spins)
+{
+    unsigned long long v = first;
+    while ((unsigned)(v >> 32) != tag) {
+        __nanosleep(20);
+        v = ld_relaxed64(p);
+        spins++;
+    }
+    return (int)(unsigned)v;
+}
+
 // same, but a miss first sleeps `backoff_ns`: the consumer drops behind its producer once and its
 // later (prefetched) reads hit, instead of re-polling L2 on the critical path of every chunk
 __device__ __forceinline__ int wait_tagged_backoff(const unsigned long long* p, unsigned long long first, unsigned tag, unsigned backoff_ns,

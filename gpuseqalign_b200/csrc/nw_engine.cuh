@@ -90,6 +90,10 @@ struct nwb200_ctx {
     int batch_maxy = 0;
     bool batch_resident = false;
     nwb::PinBuf h_batch;
+    // developer aids
+    nwb::DevBuf d_dbg;
+    bool dbg_stamps = false;
+    int dbg_mode = 0;
     // bookkeeping
     nwb200_timing timing = {};
     unsigned epoch = 0;

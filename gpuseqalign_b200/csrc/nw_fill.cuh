@@ -40,6 +40,9 @@ struct FillArgs {
     int* ticket;             // band ticket counter
     int nb;                  // number of bands
     int pad;                 // padding rows above row 1 in band 0 (nb*By - n)
+    unsigned long long* dbg; // developer aid: [nb][4] globaltimer stamps (start, prologue done, end) + poll count; nullable
+    int dbg_mode;            // developer aid: 1 = consumers do not wait (timing experiment, wrong results)
+    int slack;               // groups of head start a consumer gives its producer before it starts
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
@@ -70,6 +73,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         if (lane == 0) b = atomicAdd(a.ticket, 1);
         b = __shfl_sync(kFull, b, 0);
         if (b >= a.nb) break;
+        if (a.dbg && lane == 0) a.dbg[4 * b + 0] = globaltimer_ns();
+        unsigned spins = 0;
 
         const long long prow0 = (long long)b * By + (long long)lane * R;      // padded row index of this lane's first row
         build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
@@ -102,17 +107,23 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         __syncwarp();
         // ---- prologue: the first PD groups of the row above
         if (consumer) {
+            {   // head start for the producer: the consumer's prefetches then only touch lines that are complete
+                int c = 32 * (PD - 1 + a.slack) + 31;
+                if (c > m - 1) c = m - 1;
+                (void)wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
+            }
             for (int g = 0; g < PD; g++) {
                 const int c = 32 * g + lane;
                 if (c < m) sm.rin[c & (VR - 1)] = wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
             }
         }
         __syncwarp();
+        if (a.dbg && lane == 0) a.dbg[4 * b + 1] = globaltimer_ns();
         st.up_next = (lane == 0) ? sm.rin[0] : st.dprev;
 
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.tag = a.tag; io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
+        io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
         for (int lc = 0; lc < nlc; lc++) {
             // ---- issue the prefetches of chunk lc + PD
             const int cp = 32 * (lc + PD) + lane;
@@ -124,11 +135,19 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
             io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
-            io.hr_out = hr_out + (32 * lc - LAG);
+            io.rout_chunk = sm.rout + (lc & 1) * 32;
             sweep_chunk<R, K, 0>(st, lane, io, nullptr);
             __syncwarp();
+            // ---- publish the group of the bottom row that this chunk completed: ONE coalesced 256-byte store
+            if (lc >= SC::GL) {
+                const int v = (lane >= SC::SH) ? sm.rout[(lc & 1) * 32 + lane - SC::SH] : sm.rout[((lc + 1) & 1) * 32 + 32 - SC::SH + lane];
+                st_relaxed64(hr_out + 32 * (lc - SC::GL) + lane, pack_tagged(v, a.tag));
+            }
             // ---- land the prefetches
-            if (want_hr) sm.rin[cp & (VR - 1)] = wait_tagged(hr_in + cp, pf_hr, a.tag);
+            if (want_hr) {
+                if (a.dbg_mode == 1) sm.rin[cp & (VR - 1)] = (int)(unsigned)pf_hr;
+                else sm.rin[cp & (VR - 1)] = wait_tagged_count(hr_in + cp, pf_hr, a.tag, spins);
+            }
             else if (consumer) sm.rin[cp & (VR - 1)] = 0;
             sm.put_letter(cp, pf_x);
             // ---- snapshot of the register state for the traceback
@@ -144,6 +163,9 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             }
             __syncwarp();
         }
+        // ---- the first SH elements of the next group were produced by the last chunk (they hold the last real column)
+        if (lane < SC::SH) st_relaxed64(hr_out + 32 * (nlc - SC::GL) + lane, pack_tagged(sm.rout[((nlc - 1) & 1) * 32 + 32 - SC::SH + lane], a.tag));
+        if (a.dbg && lane == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
         // ---- every row is frozen at its last-column value by now
         if (a.lastcol != nullptr) {
             int* lp = a.lastcol + 1 + prow0;

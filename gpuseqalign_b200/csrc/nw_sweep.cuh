@@ -49,12 +49,14 @@ struct Sched {
     static constexpr int XM = 32;                      // mirror entries behind the letter ring
     static constexpr int LSTRIDE = 128 * WPL;          // bytes between the profile rows of two letters
     static constexpr int SNAP_INTS = R + 4;            // per-lane snapshot: h[R], dprev, up_next, 2 pad
+    static constexpr int GL = (LAG + 31) / 32;         // chunks until a 32-column group of the bottom row is complete
+    static constexpr int SH = 32 * GL - LAG;           // element of a group that the first step of a chunk produces
     static_assert(kPadL >= LAG + 1, "header row padding");
     __host__ __device__ static constexpr int nlc(int m) { return (m + LAG + 31) / 32; }      // 32-step chunks per band
     __host__ __device__ static constexpr size_t prof_bytes(int S) { return (size_t)(S + 1) * LSTRIDE; }
     __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
     {
-        return (prof_bytes(S) + (size_t)VR * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
+        return (prof_bytes(S) + (size_t)VR * 4 + 64 * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
     }
 };
 
@@ -75,12 +77,14 @@ struct WarpSmem {
     using SC = Sched<R, K>;
     unsigned char* prof;     // [(S+1)][32 lanes][WPL] words: bytes s'(y[row r], letter)
     int* rin;                // [VR] top-row ring: P[top][c] at (c & (VR-1))
+    int* rout;               // [64] bottom-row staging: chunk lc, step s at ((lc & 1) * 32 + s)
     unsigned short* xs;      // [XR + XM] letter ring: profile byte offset (letter * LSTRIDE) of column c at (c & (XR-1))
     __device__ __forceinline__ WarpSmem(unsigned char* base, int S)
     {
         prof = base;
         rin = reinterpret_cast<int*>(base + SC::prof_bytes(S));
-        xs = reinterpret_cast<unsigned short*>(rin + SC::VR);
+        rout = rin + SC::VR;
+        xs = reinterpret_cast<unsigned short*>(rout + 64);
     }
     __device__ __forceinline__ void put_letter(int c, unsigned off16)
     {
@@ -129,8 +133,7 @@ struct ChunkIO {
     const unsigned char* prof_lane;  // &prof[0][lane][0] as bytes
     const int* rin_chunk;            // &rin[(32*lc) & (VR-1)]: top row for lane 0, index s
     const int* rin_next;             // &rin[(32*lc + 32) & (VR-1)]: first element of the next group (K == 2 look-ahead)
-    unsigned long long* hr_out;      // MODE 0: &HR_out[32*lc - LAG] (lane 31 stores element s), nullptr = keep nothing
-    unsigned tag;                    // MODE 0: epoch tag of the tagged header elements
+    int* rout_chunk;                 // MODE 0: &rout[(lc & 1) * 32] (lane 31 stores element s), nullptr = keep nothing
     int* map_out;                    // MODE 1: &map[32*lc - LAG] (lane 31 stores element s)
     int org0;                        // MODE 1: label of the cell above lane 0 at step 0 of this chunk (= 32*lc + 1)
     unsigned char* dirs_lane;        // MODE 2: &dirs[(32*(lc-lc0))*32 + lane], one byte (R=4) / two (R=8) / four (R=16) per step
@@ -209,7 +212,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             diag = left; up = nv; st.h[r] = nv;
         }
         if constexpr (MODE == 0) {
-            if (io.hr_out != nullptr && last) st_relaxed64(io.hr_out + s, pack_tagged(st.h[R - 1], io.tag));
+            if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];
         } else if constexpr (MODE == 1) {
             if (last) io.map_out[s] = st.o[R - 1];
         } else {

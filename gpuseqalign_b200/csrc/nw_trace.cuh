@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
         st.oup_next = (lane == 0) ? 1 : 0;
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.hr_out = nullptr; io.tag = 0; io.dirs_lane = nullptr; io.negg = a.negg;
+        io.rout_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg;
         int* map_row = a.map + (long long)b * a.ldr + kPadL;
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
         }
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.hr_out = nullptr; io.tag = 0; io.map_out = nullptr; io.org0 = 0; io.negg = a.negg;
+        io.rout_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.negg = a.negg;
         for (int lc = lc0; lc <= lc_hi; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;

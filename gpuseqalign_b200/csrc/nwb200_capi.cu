@@ -123,7 +123,7 @@ void nwb200_destroy(nwb200_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
                       &c->d_map, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export,
-                      &c->d_bletters, &c->d_bmeta, &c->d_bscores})
+                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_dbg})
         b->release();
     c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -246,6 +246,11 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     if (c->epoch == 0) c->epoch = 1;
     a.tag = c->epoch; a.ticket = c->d_sync.as<int>();
     a.nb = g.nb; a.pad = g.pad;
+    a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
+    if (c->dbg_stamps) {
+        CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
+        a.dbg = c->d_dbg.as<unsigned long long>();
+    }
     int rc = launch_fill(c, a);
     if (rc) return rc;
     CU(c, cudaEventRecord(c->ev[3], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
@@ -312,6 +317,20 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
 
 #include "nwb200_capi_trace.inc"
 #include "nwb200_capi_batch.inc"
+
+// developer aid (not part of the public header): per-band globaltimer stamps of the fills that follow
+NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, unsigned long long* out, int max_bands)
+{
+    if (!c) return NWB200_ERR_INVALID_VALUE;
+    c->dbg_stamps = enable != 0; c->dbg_mode = mode;
+    if (out && c->fill_done && c->d_dbg.p) {
+        int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(out, c->d_dbg.p, sizeof(unsigned long long) * 4 * nb, cudaMemcpyDeviceToHost);
+        return nb;
+    }
+    return 0;
+}
 
 int nwb200_last_cuda_error(const nwb200_ctx* c) { return c ? (int)c->last_cuda : 0; }
 const char* nwb200_last_error(const nwb200_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
