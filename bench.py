@@ -300,7 +300,16 @@ def main():
     ms_total = max_over_ranks(ms_total)
     cells_job = sum_over_ranks(cells_rank)
     value = cells_job * steps / ms_total / 1e6
-    fill_ms = eng.timing().get("align_calc", 0.0) if args.workload == "pair16k" else ms_total / steps
+    if args.workload == "pair16k":
+        eng.fetch_score()                       # lands the CUDA-event laps of the last timed step
+        if with_trace:
+            eng.fetch_trace()
+        lap = eng.timing()
+        fill_ms = lap.get("align_calc", 0.0)
+    else:
+        eng.fetch_batch_scores()
+        lap = eng.timing()
+        fill_ms = lap.get("align_calc", 0.0)
 
     # ---- end to end through the public call with host buffers ---------------------------------
     for _ in range(2):
@@ -331,7 +340,8 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "int-issue (DPX VIMNMX3, 1 per cell; not hbm/tensor)", "achieved": achieved, "peak": peak, "unit": "GCUPS",
                          "frac": achieved / peak, "traffic": None,
-                         "kernel": "fill", "kernel_ms": fill_ms,
+                         "kernel": "nw_fill_kernel" if args.workload == "pair16k" else "nw_batch_kernel", "kernel_ms": fill_ms,
+                         "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz}}
     if world == 1 and not args.no_cpu_baseline:
