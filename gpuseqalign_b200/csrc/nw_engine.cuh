@@ -79,7 +79,8 @@ struct nwb200_ctx {
     nwb::DevBuf d_y, d_x, d_HR, d_snap, d_lastcol, d_sync;
     nwb::PinBuf h_stage, h_small, h_trace;
     // traceback
-    nwb::DevBuf d_map, d_tmeta, d_ops, d_dense, d_export;
+    nwb::DevBuf d_map, d_tmeta, d_ops, d_dense, d_export, d_HR2;
+    nwb::PinBuf h_export;
     bool trace_done = false;
     bool edit_cached = false;
     std::string last_edit;

@@ -29,6 +29,7 @@
 //                      nwtrace2_sparse.cpp:149-180 exactly: compare the NEIGHBOUR SCORES diag, up, left with
 //                      strict '<', preference diag > up > left.  In shifted coordinates H_diag vs H_up vs
 //                      H_left is (P_diag - gap) vs P_up vs P_left.
+//       3  dump        every cell value P is written to a row-major slab in HBM (score hash, header export)
 #pragma once
 #include "nw_common.cuh"
 
@@ -138,6 +139,8 @@ struct ChunkIO {
     int org0;                        // MODE 1: label of the cell above lane 0 at step 0 of this chunk (= 32*lc + 1)
     unsigned char* dirs_lane;        // MODE 2: &dirs[(32*(lc-lc0))*32 + lane], one byte (R=4) / two (R=8) / four (R=16) per step
     int negg;                        // -gap
+    int* dump_lane;                  // MODE 3: &dump[(lane*R)*dump_ld + kPadL + 32*lc - K*lane]: cell (row r, step s) at [r*dump_ld + s]
+    long long dump_ld;
 };
 
 // One 32-step chunk of one warp.
@@ -194,7 +197,8 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             const int left = st.h[r];
             const int t = add_byte(pw[s][r >> 2], 1u << (8 * (r & 3)), diag);
             const int nv = max3(t, up, left);
-            if constexpr (MODE != 0) {
+            if constexpr (MODE == 3) io.dump_lane[(long long)r * io.dump_ld + s] = nv;
+            if constexpr (MODE == 1 || MODE == 2) {
                 const int cd = diag + io.negg;            // H_diag - H_up/H_left offset: P_diag - gap
                 const bool p1 = cd < up;                  // nwtrace1_plain.cpp:57: max < up  -> move up
                 const int b1 = max(cd, up);
@@ -215,7 +219,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];
         } else if constexpr (MODE == 1) {
             if (last) io.map_out[s] = st.o[R - 1];
-        } else {
+        } else if constexpr (MODE == 2) {
             if constexpr (R == 4) io.dirs_lane[s * 32] = (unsigned char)codes;
             else if constexpr (R == 8) reinterpret_cast<unsigned short*>(io.dirs_lane)[s * 32] = (unsigned short)codes;
             else reinterpret_cast<unsigned*>(io.dirs_lane)[s * 32] = codes;

@@ -278,4 +278,110 @@ __global__ void __launch_bounds__(1024) nw_pack_kernel(const TraceArgs a)
     if (tid == 0) { a.total[0] = s_carry; a.total[1] = s_bad; }
 }
 
+
+// ---------------------------------------------------------------------------------------------- score matrix slabs
+// Re-sweeps bands b0 .. b0+nbands-1 from their header rows and writes EVERY cell (shifted value P) to a row-major
+// slab: slab[(b-b0)*By + local row][kPadL + c].  Used by the score hash (NwHash1_Plain / NwHash2_Sparse semantics,
+// nwtrace1_plain.cpp:133-154: the fold itself is sequential and done by the host as the slabs stream back) and by
+// the header export.  Bands are independent once the fill is done, so this runs at full issue rate.
+struct DumpArgs {
+    const uint8_t* y;
+    const uint8_t* x;
+    int n, m;
+    const uint8_t* sprime;
+    int S;
+    const unsigned long long* HR;
+    long long ldr;
+    int pad;
+    int b0, nbands;
+    int* slab;
+    long long ld;          // slab row pitch in ints (>= kPadL + 32*nlc)
+};
+
+template <int R, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
+{
+    using SC = Sched<R, K>;
+    constexpr int By = SC::By, PD = SC::PD, VR = SC::VR, XR = SC::XR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
+    const int m = a.m, nlc = SC::nlc(m);
+    const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
+    const int nwarps = gridDim.x * WARPS;
+    for (int bi = blockIdx.x * WARPS + w; bi < a.nbands; bi += nwarps) {
+        const int b = a.b0 + bi;
+        const long long prow0 = (long long)b * By + (long long)lane * R;
+        build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+        const unsigned long long* hr_in = (b > 0) ? a.HR + (long long)b * a.ldr + kPadL : nullptr;
+        for (int g = -2; g < PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
+        for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
+        __syncwarp();
+        for (int g = 0; g < PD; g++) load_top_group<R, K>(sm, hr_in, g, m, lane);
+        __syncwarp();
+        Lane<R, 3> st;
+#pragma unroll
+        for (int r = 0; r < R; r++) st.h[r] = 0;
+        st.dprev = 0; st.oprev = 0; st.oup_next = 0; st.o[0] = 0;
+        st.up_next = (lane == 0) ? sm.rin[0] : 0;
+        ChunkIO io;
+        io.prof_lane = sm.prof + lane * 4 * SC::WPL;
+        io.rout_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
+        io.dump_ld = a.ld;
+        int* slab_lane = a.slab + ((long long)bi * By + (long long)lane * R) * a.ld + kPadL - K * lane;
+        for (int lc = 0; lc < nlc; lc++) {
+            const int cp = 32 * (lc + PD) + lane;
+            const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
+            io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
+            io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
+            io.dump_lane = slab_lane + 32 * lc;
+            sweep_chunk<R, K, 3>(st, lane, io, nullptr);
+            __syncwarp();
+            sm.rin[cp & (VR - 1)] = pf_top;
+            sm.put_letter(cp, pf_x);
+            __syncwarp();
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------- header export
+// Reference layout (producer nwalign_gpu9_mlsp_diagdiagdiag.cu:321-359, consumer
+// nwtrace2_sparse.cpp:48-67), tiles of By x Bx aligned to the TOP-LEFT corner like the reference's:
+//   hrow[(iT*tcols + jT)*(1+Bx) + k] = H[iT*By][jT*Bx + k]      hcol[(iT*tcols + jT)*(1+By) + k] = H[iT*By + k][jT*Bx]
+// with H = P + (i+j)*gap.  Entries outside the real matrix are written as 0 (nothing consumes them).
+__global__ void nw_export_hrow_kernel(const unsigned long long* __restrict__ HR, long long ldr, int n, int m, int By, int Bx,
+                                      int trows, int tcols, int gap, int* __restrict__ hrow)
+{
+    const long long total = (long long)trows * tcols * (1 + Bx);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = e / (1 + Bx); const int k = (int)(e % (1 + Bx));
+        const int iT = (int)(t / tcols), jT = (int)(t % tcols);
+        const long long i = (long long)iT * By, j = (long long)jT * Bx + k;
+        int v = 0;
+        if (i <= n && j <= m) {
+            const int P = (i == 0 || j == 0) ? 0 : (int)(unsigned)HR[(long long)iT * ldr + kPadL + (j - 1)];
+            v = P + (int)((i + j) * gap);
+        }
+        hrow[e] = v;
+    }
+}
+// rows [r0, r0+nrows) of the matrix (1-based i = r0+1 ..) are present in `slab` (row-major, pitch ld, column c at kPadL + c)
+__global__ void nw_export_hcol_kernel(const int* __restrict__ slab, long long ld, long long r0, long long nrows, int n, int m, int By, int Bx,
+                                      int trows, int tcols, int gap, int* __restrict__ hcol, int first)
+{
+    const long long total = (long long)trows * tcols * (1 + By);
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long t = e / (1 + By); const int k = (int)(e % (1 + By));
+        const int iT = (int)(t / tcols), jT = (int)(t % tcols);
+        const long long i = (long long)iT * By + k, j = (long long)jT * Bx;
+        if (i == 0 || j == 0 || i > n || j > m) { if (first) hcol[e] = (i <= n && j <= m) ? (int)((i + j) * gap) : 0; continue; }
+        const long long lr = (i - 1) - r0;
+        if (lr < 0 || lr >= nrows) continue;
+        hcol[e] = slab[lr * ld + kPadL + (j - 1)] + (int)((i + j) * gap);
+    }
+}
+
 }  // namespace nwb

@@ -133,3 +133,44 @@ def test_error_behaviour(engine):
     with pytest.raises(NwB200Error) as ei:          # traceback needs the headers of the last fill
         engine.trace()
     assert ei.value.stat == NwStat.errorInvalidValue
+
+
+def test_golden_score_hash(engine, golden):
+    """score_hash (NwHash1_Plain / NwHash2_Sparse value): every cell recomputed on the GPU, folded by the host."""
+    for c in golden["cases"][::4]:
+        y, x = case_letters(golden, c)
+        engine.align(y, x, keep_headers=False)
+        assert f"{engine.score_hash():08x}" == c["score_hash"], (c["y"], c["x"])
+
+
+def test_score_hash_multi_band_and_variants(engine, scoring, oracle):
+    from gpuseqalign_b200 import Params, synth
+    subst = scoring["subst"]["blosum62"]
+    x = synth.letters(31, 1900); y = synth.letters(32, 1333)
+    exp = oracle.align_pair(y, x, subst, -11, want_hash=True, want_trace=False)
+    for p in (None, Params(8, 4, 256, 1), Params(16, 4, 64, 2), Params(4, 2, 32, 2)):
+        assert engine.align(y, x, keep_headers=True, params=p) == exp.score
+        assert engine.score_hash() == exp.score_hash
+
+
+@pytest.mark.parametrize("R,Bx", [(4, 64), (8, 96), (4, 512)])
+def test_exported_headers_feed_reference_style_trace(engine, golden, scoring, oracle, R, Bx):
+    """nwb200_copy_headers: headers in the reference's tile layout must let NwTrace2_Sparse (restated, and the live
+    reference when oracle/_ref was prebuilt) reproduce the golden transcript: validates every consumed header value."""
+    from gpuseqalign_b200 import Params
+    subst = scoring["subst"]["blosum62"]
+    for c in golden["cases"][::6]:
+        y, x = case_letters(golden, c)
+        score = engine.align(y, x, keep_headers=True, params=Params(R, 4, Bx, 2))
+        assert score == c["score"]
+        hrow, hcol = engine.headers()
+        info = engine.info
+        r = oracle.trace_sparse(hrow, hcol, info.tile_rows, info.tile_cols, y, x, subst, -11)
+        assert r.score == c["score"]
+        assert r.edit == c["edit"], (c["y"], c["x"])
+        if oracle.ref_available() and c["len_y"] > 100:
+            r2 = oracle.ref_trace_from_headers(y, x, subst, -11, hrow, hcol, info.tile_rows, info.tile_cols)
+            assert (r2.score, r2.edit, f"{r2.trace_hash:08x}") == (c["score"], c["edit"], c["trace_hash"])
+        # the engine's own traceback still works after an export
+        edit, th = engine.trace()
+        assert edit == c["edit"]
