@@ -1,7 +1,7 @@
 // nw_registry_b200.cpp -- getNwAlgorithmMap with the B200 entry added.
 //
 // The reference's nw_algorithm.cpp is compiled UNMODIFIED with -DgetNwAlgorithmMap=getNwAlgorithmMap_reference
-// (oracle/Makefile); this translation unit provides the symbol benchmark.cpp and cmd_parser.cpp link against and
+// (the reference build recipe); this translation unit provides the symbol benchmark.cpp and cmd_parser.cpp link against and
 // appends one line to the registry -- the whole integration a maintainer needs.
 #include "nw_algorithm.hpp"
 #include "nw_fns.hpp"
