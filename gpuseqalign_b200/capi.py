@@ -83,6 +83,7 @@ EXPORTS = [
     "nwb200_trace_pair", "nwb200_copy_headers", "nwb200_score_hash", "nwb200_align_batch", "nwb200_upload_batch",
     "nwb200_batch_resident", "nwb200_fetch_batch_scores", "nwb200_last_cuda_error", "nwb200_last_error",
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
+    "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
 ]
 
 _lib = None
@@ -128,6 +129,11 @@ def load_library():
     L.nwb200_sync.argtypes = [vp]
     L.nwb200_kernel_launches.argtypes = [vp]
     L.nwb200_version.restype = C.c_char_p
+    L.nwb200_wave_upload.argtypes = [vp, vp, i64, vp, i64, P(_Params), C.c_int, C.c_int, C.c_int]
+    L.nwb200_wave_export.argtypes = [vp, vp]
+    L.nwb200_wave_connect.argtypes = [vp, vp]
+    L.nwb200_wave_fill.argtypes = [vp, C.c_uint]
+    L.nwb200_wave_fetch.argtypes = [vp, P(C.c_int), P(i32)]
     _lib = L
     return L
 
@@ -289,6 +295,31 @@ class Engine:
                                                _ptr(scores), _ptr(edits), _ptr(edit_off), _ptr(edit_len), _ptr(hashes)))
         strs = [edits[int(edit_off[p]): int(edit_off[p]) + int(edit_len[p])].tobytes().decode("ascii") for p in range(n)]
         return scores, strs, hashes
+
+    # ---- one long pair as a cross-GPU wavefront (one Engine per rank) --------------------------
+    def wave_upload(self, y, x, rank: int, world: int, block_cols: int, params: Optional[Params] = None) -> bytes:
+        """Uploads the pair, plans the column blocks of this rank and returns the 64-byte IPC handle of its receive buffer."""
+        y = np.ascontiguousarray(y, dtype=np.uint8); x = np.ascontiguousarray(x, dtype=np.uint8)
+        p = params._c() if params else None
+        self._check(self._L.nwb200_wave_upload(self._h, _ptr(y), y.size, _ptr(x), x.size, C.byref(p) if p else None, rank, world, block_cols))
+        h = C.create_string_buffer(64)
+        self._check(self._L.nwb200_wave_export(self._h, h))
+        return h.raw
+
+    def wave_connect(self, right_peer_handle: Optional[bytes]):
+        if right_peer_handle is None:
+            self._check(self._L.nwb200_wave_connect(self._h, None))
+        else:
+            buf = C.create_string_buffer(right_peer_handle, 64)
+            self._check(self._L.nwb200_wave_connect(self._h, buf))
+
+    def wave_fill(self, epoch: int):
+        self._check(self._L.nwb200_wave_fill(self._h, epoch))
+
+    def wave_fetch(self):
+        has = C.c_int(0); s = C.c_int32(0)
+        self._check(self._L.nwb200_wave_fetch(self._h, C.byref(has), C.byref(s)))
+        return (s.value if has.value else None)
 
     # ---- introspection ------------------------------------------------------------------
     def timing(self) -> dict:

@@ -91,6 +91,12 @@ struct nwb200_ctx {
     int batch_maxy = 0;
     bool batch_resident = false;
     nwb::PinBuf h_batch;
+    // cross-GPU column-block wavefront
+    nwb::DevBuf d_wave;              // [flags (nq+1)*nb | err, pad | recv (nq+1)*recv_stride] -- ONE allocation, exported over CUDA IPC
+    void* wave_peer_base = nullptr;  // the right neighbour's d_wave mapped into this process (nullptr: loopback)
+    int wave_rank = 0, wave_world = 1, wave_wc = 0, wave_nq = 0, wave_nblocks = 0;
+    long long wave_ldr = 0, wave_hr_stride = 0, wave_recv_stride = 0;
+    bool wave_ready = false, wave_connected = false, wave_filled = false;
     // developer aids
     nwb::DevBuf d_dbg;
     bool dbg_stamps = false;

@@ -13,9 +13,12 @@
 //     (R+2 ints per lane, at a chunk boundary: nothing is checked per step).  A snapshot is the engine's
 //     "header column": the walker resumes the sweep from it to recompute a window of the band
 //     (the reference keeps rectangular header columns instead, nwalign_gpu9...cu:296-300,340-359).
-//   * Column stripes (cross-GPU wavefront): the sweep can start from the right border column of the stripe to
-//     its left (`left`, ready when left_flag[b] == tag) and leaves its own right border in `lastcol`
-//     (+ right_flag[b] = tag, stored with system scope so a peer GPU can poll it over NVLink).
+//   * Column blocks (cross-GPU wavefront for one very long pair): the columns are dealt to the ranks in blocks of wc
+//     (block g belongs to rank g % world).  A (block, band) unit starts from the right border column of the block to its
+//     left, which the owner of that block PUSHES into this rank's receive buffer with plain peer stores over NVLink
+//     followed by a system-scope release flag (st.release.sys); it pushes its own right border on to the next rank.
+//     Tickets run block-major, so one persistent launch per GPU pipelines all of its blocks: the wavefront skew is
+//     paid once, not once per block.  With world == 1 the receive buffer is the GPU's own (the same code path).
 #pragma once
 #include "nw_sweep.cuh"
 
@@ -23,21 +26,31 @@ namespace nwb {
 
 struct FillArgs {
     const uint8_t* y;        // lenY letters
-    const uint8_t* x;        // letters of this stripe's columns
-    int n, m;                // lenY, stripe width
+    const uint8_t* x;        // ALL lenX letters
+    int n, m;                // lenY, lenX
     const uint8_t* sprime;   // S*S bytes: s'[y*S+x]
     int S;                   // alphabet size (<= kMaxLetters)
-    unsigned long long* HR;  // header rows: HR[b*ldr + kPadL + c] = (tag << 32 | P[top row of band b][c+1]), b = 1..nb
-    long long ldr;           // >= kPadL + 32*nlc + 32
-    int* snap;               // snapshots: snap[((b*nsnap + k)*32 + lane)*SNAP_INTS + i] after chunk (k+1)*snap_chunks-1 (nullable)
+    unsigned long long* HR;  // header rows of column block q: HR[q*hr_stride + b*ldr + kPadL + c] = (tag << 32 | P[top row of band b][c0+c+1]), b = 1..nb
+    long long ldr;           // >= kPadL + 32*nlc(block width) + 32
+    long long hr_stride;     // elements between the header blocks of two column blocks
+    int* snap;               // snapshots: snap[((b*nsnap + k)*32 + lane)*SNAP_INTS + i] after chunk (k+1)*snap_chunks-1 (nullable; single block only)
     int nsnap;               // snapshots per band
     int snap_chunks;         // chunks between snapshots
-    const int* left;         // nullable: left[1 + padded row] = P of the column left of the stripe, left[0] = its row-0 value
-    const unsigned* left_flag;   // nullable: left_flag[b] == tag when left[] of band b is complete
-    int* lastcol;            // nullable: lastcol[1 + padded row] = P[row][last column of the stripe]
-    unsigned* right_flag;    // nullable: set to tag (system scope) after lastcol of band b is written
-    unsigned tag;            // epoch tag of this run (never 0)
-    int* ticket;             // band ticket counter
+    // ---- column blocks (cross-GPU wavefront): this rank owns blocks rank, rank+world, ... of width wc
+    int wc;                  // block width in columns (multiple of 32); single GPU, single block: wc >= m
+    int nq;                  // blocks owned by this rank
+    int rank, world;
+    int* recv;               // recv[q*recv_stride + 1 + padded row] = P of the column left of block q (recv[q*recv_stride] = row above), written by the left neighbour
+    unsigned* recv_flag;     // recv_flag[q*nb + b] == tag when band b of that column is complete
+    int* peer_recv;          // the RIGHT neighbour's recv / recv_flag (peer memory mapped over NVLink; own buffers when world == 1)
+    unsigned* peer_flag;
+    long long recv_stride;
+    int* lastcol;            // nullable: lastcol[1 + padded row] = P[row][m] (last column of the matrix), written by the owner of the last block
+    unsigned long long timeout_ns;   // give up waiting for a neighbour after this long (0 = never)
+    int* err;                // set to 1 on timeout
+    unsigned tag;            // epoch tag of this run's header rows (never 0; local to this GPU)
+    unsigned xtag;           // epoch tag of the cross-GPU border flags (the same on every rank)
+    int* ticket;             // (block, band) ticket counter
     int nb;                  // number of bands
     int pad;                 // padding rows above row 1 in band 0 (nb*By - n)
     unsigned long long* dbg; // developer aid: [nb][4] globaltimer stamps (start, prologue done, end) + poll count; nullable
@@ -64,16 +77,22 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
-    const int m = a.m;
-    const int nlc = SC::nlc(m);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
+    const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
 
     for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(a.ticket, 1);
-        b = __shfl_sync(kFull, b, 0);
-        if (b >= a.nb) break;
-        if (a.dbg && lane == 0) a.dbg[4 * b + 0] = globaltimer_ns();
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1);
+        t = __shfl_sync(kFull, t, 0);
+        if (t >= a.nb * a.nq) break;
+        const int q = t / a.nb, b = t - q * a.nb;             // tickets run block-major: (q, b-1) is always taken before (q, b)
+        const int gb = q * a.world + a.rank;                  // global column block
+        const long long c0 = (long long)gb * a.wc;            // its first column
+        const int m = (int)((a.m - c0 < a.wc) ? a.m - c0 : a.wc);
+        const int nlc = SC::nlc(m);
+        const uint8_t* xb = a.x + c0;
+        const bool has_left = gb > 0, has_right = gb + 1 < nblocks;
+        if (a.dbg && lane == 0 && q == 0) a.dbg[4 * b + 0] = globaltimer_ns();
         unsigned spins = 0;
 
         const long long prow0 = (long long)b * By + (long long)lane * R;      // padded row index of this lane's first row
@@ -82,28 +101,33 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         for (int c = -64 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
         for (int g = 0; g < PD; g++) {
             const int c = 32 * g + lane;
-            sm.put_letter(c, c < m ? (unsigned)__ldg(a.x + c) * SC::LSTRIDE : ZOFF);
+            sm.put_letter(c, c < m ? (unsigned)__ldg(xb + c) * SC::LSTRIDE : ZOFF);
         }
         for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
 
         Lane<R, 0> st;
         st.oprev = 0; st.oup_next = 0; st.o[0] = 0;
-        if (a.left != nullptr) {
-            if (a.left_flag != nullptr) {
-                while (ld_acquire_sys_u32(a.left_flag + b) != a.tag) __nanosleep(100);
+        if (has_left) {
+            // the column left of this block arrives from the left neighbour (peer stores over NVLink + system-scope flag)
+            // (band b-1's flag as well: this lane 0 reads the last row of band b-1 as its diagonal input)
+            const unsigned* fl = a.recv_flag + (long long)q * a.nb + b;
+            const unsigned long long t0 = a.timeout_ns ? globaltimer_ns() : 0ull;
+            while (ld_acquire_sys_u32(fl) != a.xtag || (b > 0 && ld_acquire_sys_u32(fl - 1) != a.xtag)) {
+                __nanosleep(200);
+                if (a.timeout_ns && globaltimer_ns() - t0 > a.timeout_ns) { if (lane == 0) atomicExch(a.err, 1); break; }
             }
-            const int* lp = a.left + 1 + prow0;
+            const int* lp = a.recv + (long long)q * a.recv_stride + 1 + prow0;
 #pragma unroll
-            for (int r = 0; r < R; r++) st.h[r] = lp[r];
-            st.dprev = lp[-1];
+            for (int r = 0; r < R; r++) st.h[r] = ld_volatile(lp + r);
+            st.dprev = ld_volatile(lp - 1);
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) st.h[r] = 0;
             st.dprev = 0;
         }
         const bool consumer = (b > 0);                 // band 0 has row 0 (P = 0) above it
-        const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
-        unsigned long long* hr_out = a.HR + (long long)(b + 1) * a.ldr + kPadL;
+        const unsigned long long* hr_in = a.HR + (long long)q * a.hr_stride + (long long)b * a.ldr + kPadL;
+        unsigned long long* hr_out = a.HR + (long long)q * a.hr_stride + (long long)(b + 1) * a.ldr + kPadL;
         __syncwarp();
         // ---- prologue: the first PD groups of the row above
         if (consumer) {
@@ -118,7 +142,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             }
         }
         __syncwarp();
-        if (a.dbg && lane == 0) a.dbg[4 * b + 1] = globaltimer_ns();
+        if (a.dbg && lane == 0 && q == 0) a.dbg[4 * b + 1] = globaltimer_ns();
         st.up_next = (lane == 0) ? sm.rin[0] : st.dprev;
 
         ChunkIO io;
@@ -130,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             unsigned long long pf_hr = 0;
             const bool want_hr = consumer && cp < m;
             if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(xb + cp) * SC::LSTRIDE : ZOFF;
             // ---- the chunk itself
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
@@ -165,17 +189,23 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         }
         // ---- the first SH elements of the next group were produced by the last chunk (they hold the last real column)
         if (lane < SC::SH) st_relaxed64(hr_out + 32 * (nlc - SC::GL) + lane, pack_tagged(sm.rout[((nlc - 1) & 1) * 32 + 32 - SC::SH + lane], a.tag));
-        if (a.dbg && lane == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
+        if (a.dbg && lane == 0 && q == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
         // ---- every row is frozen at its last-column value by now
-        if (a.lastcol != nullptr) {
+        if (has_right) {
+            // push the right border column into the right neighbour's receive buffer; its round index is q, or q+1 when we
+            // are the last rank (the next block then belongs to rank 0's next round)
+            const int qn = (a.rank + 1 == a.world) ? q + 1 : q;
+            int* lp = a.peer_recv + (long long)qn * a.recv_stride + 1 + prow0;
+#pragma unroll
+            for (int r = 0; r < R; r++) lp[r] = st.h[r];
+            if (b == 0 && lane == 0) lp[-1] = 0;                       // row above the matrix: P = 0
+            __syncwarp();
+            __threadfence_system();
+            if (lane == 0) st_release_sys_u32(a.peer_flag + (long long)qn * a.nb + b, a.xtag);
+        } else if (a.lastcol != nullptr) {
             int* lp = a.lastcol + 1 + prow0;
 #pragma unroll
             for (int r = 0; r < R; r++) lp[r] = st.h[r];
-            if (a.right_flag != nullptr) {
-                __syncwarp();
-                __threadfence_system();
-                if (lane == 0) st_release_sys_u32(a.right_flag + b, a.tag);
-            }
         }
         __syncwarp();
     }

@@ -78,7 +78,7 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     const Geometry& g = c->g;
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
-    long long ctas_needed = ((long long)g.nb + g.W - 1) / g.W;
+    long long ctas_needed = ((long long)g.nb * a.nq + g.W - 1) / g.W;
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
@@ -121,9 +121,10 @@ void nwb200_destroy(nwb200_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
                       &c->d_map, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2,
-                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_dbg})
+                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_dbg, &c->d_wave})
         b->release();
     c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release(); c->h_export.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
@@ -241,10 +242,12 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     a.HR = c->d_HR.as<unsigned long long>(); a.ldr = g.ldr;
     a.snap = (keep && g.nsnap > 0) ? c->d_snap.as<int>() : nullptr;
     a.nsnap = g.nsnap; a.snap_chunks = g.snap_chunks;
-    a.left = nullptr; a.left_flag = nullptr; a.lastcol = nullptr; a.right_flag = nullptr;
+    a.hr_stride = 0; a.wc = (g.m + 31) / 32 * 32; a.nq = 1; a.rank = 0; a.world = 1;
+    a.recv = nullptr; a.recv_flag = nullptr; a.peer_recv = nullptr; a.peer_flag = nullptr; a.recv_stride = 0;
+    a.lastcol = nullptr; a.timeout_ns = 0; a.err = nullptr;
     c->epoch++;
     if (c->epoch == 0) c->epoch = 1;
-    a.tag = c->epoch; a.ticket = c->d_sync.as<int>();
+    a.tag = c->epoch; a.xtag = 0; a.ticket = c->d_sync.as<int>();
     a.nb = g.nb; a.pad = g.pad;
     a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
     if (c->dbg_stamps) {
@@ -317,6 +320,7 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
 
 #include "nwb200_capi_trace.inc"
 #include "nwb200_capi_batch.inc"
+#include "nwb200_capi_wave.inc"
 
 // developer aid (not part of the public header): per-band globaltimer stamps of the fills that follow
 NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, unsigned long long* out, int max_bands)

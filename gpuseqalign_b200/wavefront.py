@@ -1,0 +1,33 @@
+"""One very long pair across the GPUs of one box: the host side of the column-block wavefront (BASELINE configs 4, 5).
+
+One process per GPU (torch.distributed).  The only things that cross the process group are the 64-byte CUDA IPC
+handles of the receive buffers (setup), a barrier, and the final 4-byte score; the border columns themselves move
+GPU-to-GPU as peer stores issued by the fill kernel (csrc/nw_fill.cuh), not through NCCL.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+
+def wave_align(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: int = 1, block_cols: int = 2048,
+               epoch: int = 1, params=None, group=None) -> int:
+    """Score of NW(y, x); every rank passes the same y, x, block_cols and epoch and gets the same score back."""
+    handle = engine.wave_upload(y, x, rank, world, block_cols, params)
+    if world == 1:
+        engine.wave_connect(None)
+        engine.wave_fill(epoch)
+        return engine.wave_fetch()
+    import torch
+    import torch.distributed as dist
+    handles: list = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    engine.wave_connect(handles[(rank + 1) % world])
+    dist.barrier(group=group)                       # every receive buffer exists and is mapped before anyone pushes into it
+    engine.wave_fill(epoch)
+    score = engine.wave_fetch()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([score if score is not None else -(2 ** 62)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())

@@ -154,6 +154,21 @@ NWB200_API int  nwb200_upload_batch(nwb200_ctx* ctx, const uint8_t* letters, siz
 NWB200_API int  nwb200_batch_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
 NWB200_API int  nwb200_fetch_batch_scores(nwb200_ctx* ctx, int32_t* scores); /* syncs */
 
+/* One very long pair as a cross-GPU wavefront (BASELINE configs 4 and 5; no reference counterpart -- the reference
+ * is single-GPU, benchmark.cpp:179).  One context per GPU / process; the columns are dealt to the ranks in blocks of
+ * block_cols; border columns travel GPU-to-GPU as peer stores over NVLink into the neighbour's receive buffer, which
+ * is shared through a 64-byte CUDA IPC handle:
+ *   every rank: nwb200_wave_upload -> nwb200_wave_export(handle) -> [exchange handles] ->
+ *               nwb200_wave_connect(handle of rank (r+1) % world; NULL when world == 1) -> [barrier] ->
+ *               nwb200_wave_fill(epoch, same non-zero value on every rank) -> nwb200_wave_fetch.
+ * The score is returned by the rank that owns the last column block (*has_score = 1). */
+NWB200_API int  nwb200_wave_upload(nwb200_ctx* ctx, const uint8_t* y, int64_t len_y, const uint8_t* x, int64_t len_x,
+                                   const nwb200_params* params, int rank, int world, int block_cols);
+NWB200_API int  nwb200_wave_export(nwb200_ctx* ctx, void* handle64);
+NWB200_API int  nwb200_wave_connect(nwb200_ctx* ctx, const void* right_peer_handle64);
+NWB200_API int  nwb200_wave_fill(nwb200_ctx* ctx, unsigned epoch);           /* async on the ctx stream */
+NWB200_API int  nwb200_wave_fetch(nwb200_ctx* ctx, int* has_score, int32_t* align_cost);   /* syncs */
+
 /* Introspection. */
 NWB200_API int         nwb200_last_cuda_error(const nwb200_ctx* ctx);
 NWB200_API const char* nwb200_last_error(const nwb200_ctx* ctx);

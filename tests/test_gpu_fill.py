@@ -174,3 +174,16 @@ def test_exported_headers_feed_reference_style_trace(engine, golden, scoring, or
         # the engine's own traceback still works after an export
         edit, th = engine.trace()
         assert edit == c["edit"]
+
+
+@pytest.mark.parametrize("R,block", [(4, 256), (8, 64), (4, 2048), (16, 32)])
+def test_column_block_wavefront_loopback(engine, scoring, oracle, R, block):
+    """The cross-GPU wavefront code path with world = 1: the blocks hand their border columns to each other through the
+    GPU's own receive buffer (same kernel, same flags as over NVLink)."""
+    from gpuseqalign_b200 import Params, synth
+    from gpuseqalign_b200.wavefront import wave_align
+    subst = scoring["subst"]["blosum62"]
+    for n, m, seed in [(300, 5000, 41), (1000, 777, 43), (1, 100, 45), (130, 33, 47)]:
+        y = synth.letters(seed, n); x = synth.letters(seed + 1, m)
+        exp, _, _, _ = oracle.fill_rolling(y, x, subst, -11)
+        assert wave_align(engine, y, x, block_cols=block, epoch=seed, params=Params(R, 4, 0, 2)) == exp, (n, m)
