@@ -82,6 +82,8 @@ struct nwb200_ctx {
     nwb::DevBuf d_map, d_tmeta, d_ops, d_dense, d_export, d_HR2;
     nwb::PinBuf h_export;
     bool trace_done = false;
+    bool map_valid = false;          // the last fill launch also produced the origin maps
+    bool fuse_map = true;
     bool edit_cached = false;
     std::string last_edit;
     unsigned last_hash = 0;

@@ -56,6 +56,10 @@ struct FillArgs {
     unsigned long long* dbg; // developer aid: [nb][4] globaltimer stamps (start, prologue done, end) + poll count; nullable
     int dbg_mode;            // developer aid: 1 = consumers do not wait (timing experiment, wrong results)
     int slack;               // groups of head start a consumer gives its producer before it starts
+    int pd;                  // header-row groups prefetched ahead (2: the K == 2 look-ahead reads the first element of the next group)
+    int* map;                // nullable (single block only): origin maps for the traceback, computed IN THIS LAUNCH by extra
+                             // warps that follow the fill one band behind (map[b*ldr + kPadL + c], see nw_trace.cuh pass A)
+    int negg;                // -gap (map units)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
@@ -69,14 +73,76 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Origin map of one band (traceback pass A, see nw_trace.cuh) computed inside the fill launch: the warp follows the
+// fill one band behind, consuming the same tagged header row the fill unit of this band consumes.
+template <int R, int K>
+__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const int b, const int lane)
+{
+    using SC = Sched<R, K>;
+    constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
+    const int PD = a.pd;
+    const int m = a.m, nlc = SC::nlc(m);
+    const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
+    const long long prow0 = (long long)b * By + (long long)lane * R;
+    build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+    const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
+    for (int c = -64 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
+    for (int g = 0; g < PD; g++) {
+        const int c = 32 * g + lane;
+        sm.put_letter(c, c < m ? (unsigned)__ldg(a.x + c) * SC::LSTRIDE : ZOFF);
+    }
+    for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
+    __syncwarp();
+    {
+        int c = 32 * (PD - 1 + a.slack) + 31;
+        if (c > m - 1) c = m - 1;
+        (void)wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
+    }
+    for (int g = 0; g < PD; g++) {
+        const int c = 32 * g + lane;
+        if (c < m) sm.rin[c & (VR - 1)] = wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
+    }
+    __syncwarp();
+    Lane<R, 1> st;
+#pragma unroll
+    for (int r = 0; r < R; r++) { st.h[r] = 0; st.o[r] = 0; }
+    st.dprev = 0; st.oprev = 0;
+    st.up_next = (lane == 0) ? sm.rin[0] : 0;
+    st.oup_next = (lane == 0) ? 1 : 0;
+    ChunkIO io;
+    io.prof_lane = sm.prof + lane * 4 * SC::WPL;
+    io.rout_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg; io.dump_lane = nullptr; io.dump_ld = 0;
+    int* map_row = a.map + (long long)b * a.ldr + kPadL;
+    for (int lc = 0; lc < nlc; lc++) {
+        const int cp = 32 * (lc + PD) + lane;
+        unsigned long long pf_hr = 0;
+        const bool want_hr = cp < m;
+        if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
+        const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+        io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
+        io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
+        io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
+        io.map_out = map_row + (32 * lc - LAG);
+        io.org0 = 32 * lc + 1;
+        sweep_chunk<R, K, 1>(st, lane, io, nullptr);
+        __syncwarp();
+        sm.rin[cp & (VR - 1)] = want_hr ? wait_tagged(hr_in + cp, pf_hr, a.tag) : 0;
+        sm.put_letter(cp, pf_x);
+        __syncwarp();
+    }
+}
+
 template <int R, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
 {
     using SC = Sched<R, K>;
-    constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
+    constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
+    const int PD = a.pd;
+    const bool with_map = a.map != nullptr;
+    const int nunits = with_map ? 2 * a.nb - 1 : a.nb * a.nq;
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
     const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
 
@@ -84,7 +150,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         int t = 0;
         if (lane == 0) t = atomicAdd(a.ticket, 1);
         t = __shfl_sync(kFull, t, 0);
-        if (t >= a.nb * a.nq) break;
+        if (t >= nunits) break;
+        if (with_map && t > 0 && (t & 1) == 0) {              // ticket 2k: origin map of band k (its input, header row k, comes from fill unit k-1)
+            map_unit<R, K>(a, sm, t >> 1, lane);
+            continue;
+        }
+        if (with_map) t = (t + 1) >> 1;                       // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
         const int q = t / a.nb, b = t - q * a.nb;             // tickets run block-major: (q, b-1) is always taken before (q, b)
         const int gb = q * a.world + a.rank;                  // global column block
         const long long c0 = (long long)gb * a.wc;            // its first column
@@ -147,7 +218,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
 
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
+        io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0;
         for (int lc = 0; lc < nlc; lc++) {
             // ---- issue the prefetches of chunk lc + PD
             const int cp = 32 * (lc + PD) + lane;

@@ -78,7 +78,7 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     const Geometry& g = c->g;
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
-    long long ctas_needed = ((long long)g.nb * a.nq + g.W - 1) / g.W;
+    long long ctas_needed = ((a.map ? 2LL * g.nb - 1 : (long long)g.nb * a.nq) + g.W - 1) / g.W;
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
@@ -249,6 +249,13 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     if (c->epoch == 0) c->epoch = 1;
     a.tag = c->epoch; a.xtag = 0; a.ticket = c->d_sync.as<int>();
     a.nb = g.nb; a.pad = g.pad;
+    a.pd = 2; a.negg = -c->gap; a.map = nullptr;
+    // the origin maps of the traceback ride along in the fill launch while every unit still gets an SM sub-partition of its own
+    if (keep && c->fuse_map && g.nb > 1 && 2LL * g.nb - 1 <= 4LL * c->sm_count) {
+        CU(c, c->d_map.ensure(sizeof(int) * (size_t)g.nb * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc maps");
+        a.map = c->d_map.as<int>();
+    }
+    c->map_valid = a.map != nullptr;
     a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
     if (c->dbg_stamps) {
         CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
@@ -326,7 +333,8 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
 NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, unsigned long long* out, int max_bands)
 {
     if (!c) return NWB200_ERR_INVALID_VALUE;
-    c->dbg_stamps = enable != 0; c->dbg_mode = mode;
+    c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
+    c->fuse_map = (enable & 4) == 0;
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);

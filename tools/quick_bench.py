@@ -15,6 +15,10 @@ def main():
     subst = np.array(sc["subst"]["blosum62"], dtype=np.int32)
     e = Engine(0)
     e.set_scoring(subst, -11)
+    if os.environ.get('DBG'):      # bit 1: prefetch distance 1, bit 2: origin maps in a separate launch (see nwb200_debug_band_stamps)
+        import ctypes as C
+        e._L.nwb200_debug_band_stamps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        e._L.nwb200_debug_band_stamps(e._h, int(os.environ['DBG']), 0, None, 0)
     shapes = [(16384, 16384)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
     for n, m in shapes:
         y = synth.letters(2002, n); x = synth.letters(2001, m)
