@@ -263,6 +263,7 @@ def main():
         per = args.pairs // world
         first = rank * per
         pool, offY, lenY, offX, lenX = synth.batch_pairs(first, per, 256, 256)
+        pool = torch.from_numpy(pool).pin_memory().numpy()          # e2e: H2D from pinned host memory
         cells_rank = float(per) * 256.0 * 256.0
         eng.upload_batch(pool, offY, lenY, offX, lenX)
 

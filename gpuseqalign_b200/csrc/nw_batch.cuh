@@ -16,12 +16,14 @@ struct BatchArgs {
     const unsigned* lenY;
     const unsigned long long* offX;      // ... and of the column sequence
     const unsigned* lenX;
+    unsigned long long first;            // this launch aligns pairs [first, npairs)
     unsigned long long npairs;
     const uint8_t* sprime;
     int S;
     int gap;
     int* scores;                         // H[lenY][lenX] per pair; kBatchTooTall if lenY > 32*R (the host re-runs those as single pairs)
-    unsigned long long* ticket;
+    unsigned long long* ticket;          // zero at launch
+    int* err;                            // set to 1 when a letter outside the alphabet is met (the pair's score is then meaningless)
 };
 
 constexpr int kBatchTooTall = (int)0x80000000;
@@ -33,6 +35,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
     using SC = Sched<R, K>;
     constexpr int By = SC::By, PD = SC::PD, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
@@ -43,7 +47,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
 
     for (;;) {
         unsigned long long p = 0;
-        if (lane == 0) p = atomicAdd(a.ticket, 1ull);
+        if (lane == 0) p = a.first + atomicAdd(a.ticket, 1ull);
         p = __shfl_sync(kFull, p, 0);
         if (p >= a.npairs) break;
         const int n = (int)a.lenY[p], m = (int)a.lenX[p];
@@ -53,11 +57,18 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         const uint8_t* x = a.letters + a.offX[p];
         const int pad = By - n;                                    // rows are aligned to the bottom of the band
         __syncwarp();
-        build_profile<R, K>(sm, a.sprime, a.S, y, (long long)lane * R - pad, n, lane, nullptr);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane * R - pad + r;
+            if (i >= 0 && i < n && (unsigned)__ldg(y + i) >= (unsigned)a.S) *a.err = 1;
+        }
+        build_profile<R, K>(sm, sp_tab, a.S, y, (long long)lane * R - pad, n, lane, nullptr);
         for (int c = -32 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
         for (int g = 0; g < PD; g++) {
             const int c = 32 * g + lane;
-            sm.put_letter(c, c < m ? (unsigned)__ldg(x + c) * SC::LSTRIDE : ZOFF);
+            unsigned v = c < m ? (unsigned)__ldg(x + c) : (unsigned)a.S;
+            if (v > (unsigned)a.S) { v = (unsigned)a.S; *a.err = 1; }
+            sm.put_letter(c, v * SC::LSTRIDE);
         }
         __syncwarp();
         Lane<R, 0> st;
@@ -67,7 +78,9 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         const int nlc = SC::nlc(m);
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) * SC::LSTRIDE : ZOFF;
+            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : (unsigned)a.S;
+            if (pf_x > (unsigned)a.S) { pf_x = (unsigned)a.S; *a.err = 1; }
+            pf_x *= SC::LSTRIDE;
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             sweep_chunk<R, K, 0, false>(st, lane, io, nullptr);
             __syncwarp();

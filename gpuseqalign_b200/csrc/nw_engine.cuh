@@ -88,7 +88,9 @@ struct nwb200_ctx {
     std::string last_edit;
     unsigned last_hash = 0;
     // batch
-    nwb::DevBuf d_bletters, d_bmeta, d_bscores;
+    nwb::DevBuf d_bletters, d_bmeta, d_bscores, d_bticket;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t slice_ev[48] = {};
     size_t batch_pairs = 0, batch_letters = 0;
     int batch_maxy = 0;
     bool batch_resident = false;

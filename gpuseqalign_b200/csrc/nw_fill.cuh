@@ -76,7 +76,7 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v)
 // Origin map of one band (traceback pass A, see nw_trace.cuh) computed inside the fill launch: the warp follows the
 // fill one band behind, consuming the same tagged header row the fill unit of this band consumes.
 template <int R, int K>
-__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const int b, const int lane)
+__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const unsigned* sp_tab, const int b, const int lane)
 {
     using SC = Sched<R, K>;
     constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     const int m = a.m, nlc = SC::nlc(m);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     const long long prow0 = (long long)b * By + (long long)lane * R;
-    build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+    build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
     const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
     for (int c = -64 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
     for (int g = 0; g < PD; g++) {
@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
     using SC = Sched<R, K>;
     constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int PD = a.pd;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         t = __shfl_sync(kFull, t, 0);
         if (t >= nunits) break;
         if (with_map && t > 0 && (t & 1) == 0) {              // ticket 2k: origin map of band k (its input, header row k, comes from fill unit k-1)
-            map_unit<R, K>(a, sm, t >> 1, lane);
+            map_unit<R, K>(a, sm, sp_tab, t >> 1, lane);
             continue;
         }
         if (with_map) t = (t + 1) >> 1;                       // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         unsigned spins = 0;
 
         const long long prow0 = (long long)b * By + (long long)lane * R;      // padded row index of this lane's first row
-        build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+        build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
         // letter ring: columns -64..-1 use the zero row, groups 0..PD-1 are loaded now
         for (int c = -64 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
         for (int g = 0; g < PD; g++) {

@@ -95,10 +95,25 @@ struct WarpSmem {
     }
 };
 
-// Per-lane packed profile for the band's rows; row S is the all-zero row used outside the sequence.
+// CTA-wide copy of the byte table s'[y][x] in shared memory: rows of 17 words (68 bytes: conflict-free when the lanes
+// of a warp read the same column group of 32 different rows), row S is all zero (padding rows).
+constexpr int kSpPitch = 17;                              // words per row
+constexpr int kSpWords = (kMaxLetters + 1) * kSpPitch;    // static shared memory of every kernel that builds profiles
+__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S)
+{
+    for (int i = threadIdx.x; i < kSpWords; i += blockDim.x) sp_tab[i] = 0u;
+    __syncthreads();
+    unsigned char* t = reinterpret_cast<unsigned char*>(sp_tab);
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) t[(i / S) * (kSpPitch * 4) + (i % S)] = __ldg(sprime + i);
+    __syncthreads();
+}
+
+// Per-lane packed profile for the band's rows: prof[letter][lane][q] = bytes s'(y[row 4q+0..3], letter); row S of prof is
+// the all-zero row used outside the sequence.  Four table rows (one per matrix row) are read a word (4 letters) at a
+// time and transposed with byte permutes: 16 instructions per 4 letters and 4 rows.
 // yrow0 = 0-based index into y of this lane's first row (negative / >= n: padding row, zero bytes).
 template <int R, int K>
-__device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const uint8_t* __restrict__ sprime, int S,
+__device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const unsigned* __restrict__ sp_tab, int S,
                                               const uint8_t* __restrict__ y, long long yrow0, long long n, int lane, unsigned* yl_out)
 {
     using SC = Sched<R, K>;
@@ -111,21 +126,28 @@ __device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const ui
         if (yl_out) yl_out[r] = yl[r];
     }
     unsigned* pl = reinterpret_cast<unsigned*>(sm.prof) + lane * WPL;
-    for (int xl = 0; xl < S; xl++) {
 #pragma unroll
-        for (int q = 0; q < WPL; q++) {
-            unsigned word = 0;
+    for (int q = 0; q < WPL; q++) {
+        const unsigned* row[4];
 #pragma unroll
-            for (int r = 0; r < 4; r++) {
-                const unsigned yy = yl[q * 4 + r];
-                const unsigned b = (yy != 0xffu) ? (unsigned)__ldg(sprime + yy * S + xl) : 0u;
-                word |= b << (8 * r);
-            }
-            pl[(size_t)xl * 32 * WPL + q] = word;
+        for (int r = 0; r < 4; r++) {
+            const unsigned yy = yl[q * 4 + r];
+            row[r] = sp_tab + (yy != 0xffu && yy < (unsigned)S ? yy : (unsigned)S) * kSpPitch;
         }
+        for (int g4 = 0; 4 * g4 < S; g4++) {
+            const unsigned w0 = row[0][g4], w1 = row[1][g4], w2 = row[2][g4], w3 = row[3][g4];
+            const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+            const unsigned t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+            const unsigned o0 = __byte_perm(t0, t1, 0x5410), o1 = __byte_perm(t0, t1, 0x7632);
+            const unsigned o2 = __byte_perm(t2, t3, 0x5410), o3 = __byte_perm(t2, t3, 0x7632);
+            const int xl = 4 * g4;
+            pl[(size_t)(xl + 0) * 32 * WPL + q] = o0;
+            if (xl + 1 < S) pl[(size_t)(xl + 1) * 32 * WPL + q] = o1;
+            if (xl + 2 < S) pl[(size_t)(xl + 2) * 32 * WPL + q] = o2;
+            if (xl + 3 < S) pl[(size_t)(xl + 3) * 32 * WPL + q] = o3;
+        }
+        pl[(size_t)S * 32 * WPL + q] = 0u;
     }
-#pragma unroll
-    for (int q = 0; q < WPL; q++) pl[(size_t)S * 32 * WPL + q] = 0u;
 }
 
 // What one chunk reads and writes besides the lane state.

@@ -65,6 +65,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     using SC = Sched<R, K>;
     constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int m = a.m, nlc = SC::nlc(m);
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     // band 0 needs no map: the walker of band 0 ends the path itself
     for (int b = 1 + blockIdx.x * WARPS + w; b < a.nb; b += nwarps) {
         const long long prow0 = (long long)b * By + (long long)lane * R;
-        build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+        build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
         const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
         for (int g = -2; g < PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
         for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
@@ -135,6 +137,8 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
     constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
     constexpr int DB = R / 4;                                  // bytes of move codes per lane and step
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S);
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     WarpSmem<R, K> sm(smem_raw, a.S);
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     const long long prow0 = (long long)b * By + (long long)lane * R;
     unsigned yl[R], yoff[R];
-    build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, yl);
+    build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, yl);
 #pragma unroll
     for (int r = 0; r < R; r++) yoff[r] = yl[r] * SC::LSTRIDE;
     const unsigned long long* hr_in = (b > 0) ? a.HR + (long long)b * a.ldr + kPadL : nullptr;
@@ -304,6 +308,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
     using SC = Sched<R, K>;
     constexpr int By = SC::By, PD = SC::PD, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int m = a.m, nlc = SC::nlc(m);
@@ -312,7 +318,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
     for (int bi = blockIdx.x * WARPS + w; bi < a.nbands; bi += nwarps) {
         const int b = a.b0 + bi;
         const long long prow0 = (long long)b * By + (long long)lane * R;
-        build_profile<R, K>(sm, a.sprime, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
+        build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
         const unsigned long long* hr_in = (b > 0) ? a.HR + (long long)b * a.ldr + kPadL : nullptr;
         for (int g = -2; g < PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
         for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;

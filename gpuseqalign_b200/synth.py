@@ -34,16 +34,7 @@ def mutated_copy(x: np.ndarray, seed: int, target_len: int) -> np.ndarray:
     (random residue, then the original), u < 150 substitution, else copy; truncate / pad to target_len."""
     out = []
     s = seed & 0xFFFFFFFFFFFFFFFF
-    pos = 0
-
-    def nxt():
-        nonlocal pos
-        v = int(splitmix64(s, 1, pos)[0])
-        pos += 1
-        return v
-
-    # vectorised draw of the decision stream would change the stream order of the inserted residues,
-    # so this stays a simple loop over blocks of pre-drawn numbers
+    # one stream of draws, consumed in order (decision, then the random residue when one is needed)
     draws = splitmix64(s, 2 * len(x) + 2 * target_len + 16)
     di = 0
     for r in x:
@@ -63,13 +54,13 @@ def mutated_copy(x: np.ndarray, seed: int, target_len: int) -> np.ndarray:
 
 
 def batch_pairs(first_pair: int, n_pairs: int, len_y: int, len_x: int):
-    """cfg3 batch: pair p has X seed 3e6+2p and Y seed 3e6+2p+1.  Returns (letters, offY, lenY, offX, lenX)
-    with all X sequences first, then all Y sequences, in one byte pool."""
-    pool = np.empty(n_pairs * (len_x + len_y), dtype=np.uint8)
-    # one stream per sequence; vectorised over pairs
+    """cfg3 batch: pair p has X seed 3e6+2p and Y seed 3e6+2p+1.  Returns (letters, offY, lenY, offX, lenX); the byte pool
+    holds the pairs one after the other ([X_p | Y_p]), so a prefix of the pool is a prefix of the batch."""
+    stride = len_x + len_y
+    pool = np.empty((n_pairs, stride), dtype=np.uint8)
     with np.errstate(over="ignore"):
         p = np.arange(first_pair, first_pair + n_pairs, dtype=np.uint64)
-        for which, ln, base in ((0, len_x, 0), (1, len_y, n_pairs * len_x)):
+        for which, ln, col in ((0, len_x, 0), (1, len_y, len_x)):
             seeds = np.uint64(3_000_000) + np.uint64(2) * p + np.uint64(which)
             k = np.arange(1, ln + 1, dtype=np.uint64)
             chunk = max(1, (1 << 22) // max(ln, 1))
@@ -79,9 +70,9 @@ def batch_pairs(first_pair: int, n_pairs: int, len_y: int, len_x: int):
                 z = (z ^ (z >> np.uint64(30))) * _M1
                 z = (z ^ (z >> np.uint64(27))) * _M2
                 z = z ^ (z >> np.uint64(31))
-                pool[base + lo * ln: base + hi * ln] = ((z >> np.uint64(33)) % np.uint64(20)).astype(np.uint8).ravel()
-    offX = (np.arange(n_pairs, dtype=np.uint64) * np.uint64(len_x))
-    offY = np.uint64(n_pairs * len_x) + np.arange(n_pairs, dtype=np.uint64) * np.uint64(len_y)
+                pool[lo:hi, col:col + ln] = ((z >> np.uint64(33)) % np.uint64(20)).astype(np.uint8)
+    offX = np.arange(n_pairs, dtype=np.uint64) * np.uint64(stride)
+    offY = offX + np.uint64(len_x)
     lenX = np.full(n_pairs, len_x, dtype=np.uint32)
     lenY = np.full(n_pairs, len_y, dtype=np.uint32)
-    return pool, offY, lenY, offX, lenX
+    return pool.reshape(-1), offY, lenY, offX, lenX

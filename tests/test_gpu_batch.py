@@ -67,3 +67,29 @@ def test_batch_resident_split_form(engine, scoring, oracle):
     for _ in range(3):
         engine.batch_resident()
         assert np.array_equal(engine.fetch_batch_scores(), exp)
+
+
+def test_batch_rejects_letters_outside_the_alphabet(engine):
+    from gpuseqalign_b200 import NwB200Error, NwStat, synth
+    pool, offY, lenY, offX, lenX = synth.batch_pairs(0, 50, 64, 64)
+    pool = pool.copy(); pool[1234] = 77
+    with pytest.raises(NwB200Error) as ei:
+        engine.align_batch(pool, offY, lenY, offX, lenX)
+    assert ei.value.stat == NwStat.errorInvalidValue
+    bad_off = offY.copy(); bad_off[3] = pool.size
+    with pytest.raises(NwB200Error):
+        engine.align_batch(pool, bad_off, lenY, offX, lenX)
+
+
+def test_batch_pinned_and_pageable_sources_agree(engine, scoring, oracle):
+    """The one-shot call pipelines H2D slices with the kernel; pinned memory goes by DMA, pageable through a staging ring."""
+    import torch
+    from gpuseqalign_b200 import synth
+    subst = scoring["subst"]["blosum62"]
+    pool, offY, lenY, offX, lenX = synth.batch_pairs(7, 140000, 256, 256)        # 71 MB: several slices
+    exp = oracle.score_batch(pool[: 4000 * 512], offY[:4000], lenY[:4000], offX[:4000], lenX[:4000], subst, -11)
+    a = engine.align_batch(pool, offY, lenY, offX, lenX)
+    pinned = torch.from_numpy(pool).pin_memory().numpy()
+    b = engine.align_batch(pinned, offY, lenY, offX, lenX)
+    assert np.array_equal(a, b) and np.array_equal(a[:4000], exp)
+    assert int(a.astype(np.int64).sum()) == int(b.astype(np.int64).sum())
