@@ -84,6 +84,7 @@ EXPORTS = [
     "nwb200_batch_resident", "nwb200_fetch_batch_scores", "nwb200_last_cuda_error", "nwb200_last_error",
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
+    "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch",
 ]
 
 _lib = None
@@ -134,6 +135,9 @@ def load_library():
     L.nwb200_wave_connect.argtypes = [vp, vp]
     L.nwb200_wave_fill.argtypes = [vp, C.c_uint]
     L.nwb200_wave_fetch.argtypes = [vp, P(C.c_int), P(i32)]
+    L.nwb200_scan_upload.argtypes = [vp, vp, i64, vp, i64, C.c_int, C.c_int]
+    L.nwb200_scan_fill.argtypes = [vp, C.c_uint]
+    L.nwb200_scan_fetch.argtypes = [vp, P(C.c_int), P(i32)]
     _lib = L
     return L
 
@@ -319,6 +323,21 @@ class Engine:
     def wave_fetch(self):
         has = C.c_int(0); s = C.c_int32(0)
         self._check(self._L.nwb200_wave_fetch(self._h, C.byref(has), C.byref(s)))
+        return (s.value if has.value else None)
+
+    def scan_upload(self, y, x, rank: int, world: int) -> bytes:
+        y = np.ascontiguousarray(y, dtype=np.uint8); x = np.ascontiguousarray(x, dtype=np.uint8)
+        self._check(self._L.nwb200_scan_upload(self._h, _ptr(y), y.size, _ptr(x), x.size, rank, world))
+        h = C.create_string_buffer(64)
+        self._check(self._L.nwb200_wave_export(self._h, h))
+        return h.raw
+
+    def scan_fill(self, epoch: int):
+        self._check(self._L.nwb200_scan_fill(self._h, epoch))
+
+    def scan_fetch(self):
+        has = C.c_int(0); s = C.c_int32(0)
+        self._check(self._L.nwb200_scan_fetch(self._h, C.byref(has), C.byref(s)))
         return (s.value if has.value else None)
 
     # ---- introspection ------------------------------------------------------------------

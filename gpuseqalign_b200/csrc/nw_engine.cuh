@@ -101,6 +101,10 @@ struct nwb200_ctx {
     int wave_rank = 0, wave_world = 1, wave_wc = 0, wave_nq = 0, wave_nblocks = 0;
     long long wave_ldr = 0, wave_hr_stride = 0, wave_recv_stride = 0;
     bool wave_ready = false, wave_connected = false, wave_filled = false;
+    // row-parallel prefix-max scorer
+    int scan_total = 0, scan_chunk0 = 0, scan_nchunks = 0, scan_per = 0;
+    unsigned scan_epoch = 0;
+    bool scan_ready = false, scan_filled = false;
     // developer aids
     nwb::DevBuf d_dbg;
     bool dbg_stamps = false;

@@ -8,6 +8,7 @@
 #include "nw_fill.cuh"
 #include "nw_trace.cuh"
 #include "nw_batch.cuh"
+#include "nw_scan.cuh"
 
 using namespace nwb;
 
@@ -330,6 +331,7 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
 #include "nwb200_capi_trace.inc"
 #include "nwb200_capi_batch.inc"
 #include "nwb200_capi_wave.inc"
+#include "nwb200_capi_scan.inc"
 
 // developer aid (not part of the public header): per-band globaltimer stamps of the fills that follow
 NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, unsigned long long* out, int max_bands)

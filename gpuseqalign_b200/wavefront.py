@@ -31,3 +31,25 @@ def wave_align(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: in
     t = torch.tensor([score if score is not None else -(2 ** 62)], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return int(t.item())
+
+
+def scan_align(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: int = 1, epoch: int = 1, group=None) -> int:
+    """Score of NW(y, x) for a matrix with few rows and very many columns (row-parallel prefix max, csrc/nw_scan.cuh);
+    the chunks of 4096 columns are dealt to the ranks in contiguous ranges.  Same calling convention as wave_align."""
+    handle = engine.scan_upload(y, x, rank, world)
+    if world == 1:
+        engine.wave_connect(None)
+        engine.scan_fill(epoch)
+        return engine.scan_fetch()
+    import torch
+    import torch.distributed as dist
+    handles: list = [None] * world
+    dist.all_gather_object(handles, handle, group=group)
+    engine.wave_connect(handles[(rank + 1) % world])
+    dist.barrier(group=group)
+    engine.scan_fill(epoch)
+    score = engine.scan_fetch()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    t = torch.tensor([score if score is not None else -(2 ** 62)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())

@@ -125,3 +125,20 @@ def test_batch_checksum_full_cfg3_slice(engine, scoring, oracle):
         y = pool[int(offY[p]): int(offY[p]) + 256]; x = pool[int(offX[p]): int(offX[p]) + 256]
         s2, ci, cj, ok = rescore_transcript(edits[p], y, x, subst, -11)
         assert ok and (ci, cj) == (256, 256) and sc[p] == exp[p]
+
+
+def test_prefix_max_scorer_small_shapes(engine, scoring, oracle):
+    """Row-parallel prefix-max formulation (nw_scan.cuh) vs the oracle: chunk boundaries, single rows, many chunks."""
+    from gpuseqalign_b200 import synth
+    from gpuseqalign_b200.wavefront import scan_align
+    subst = scoring["subst"]["blosum62"]
+    for n, m, seed in [(1, 1, 1), (3, 4095, 2), (5, 4096, 3), (7, 4097, 4), (64, 20000, 5), (300, 70000, 6), (2048, 9000, 7), (17, 300000, 8)]:
+        y = synth.letters(100 + seed, n); x = synth.letters(200 + seed, m)
+        exp, _, _, _ = oracle.fill_rolling(y, x, subst, -11)
+        assert scan_align(engine, y, x, epoch=seed) == exp, (n, m)
+
+
+def test_cfg4_prefix_max_scorer(engine, big):
+    from gpuseqalign_b200.wavefront import scan_align
+    y, x = _inputs("cfg4")
+    assert scan_align(engine, y, x, epoch=44) == big["cfg4"]["score"]

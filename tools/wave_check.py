@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 from gpuseqalign_b200 import Engine, Params, synth
-from gpuseqalign_b200.wavefront import wave_align
+from gpuseqalign_b200.wavefront import wave_align, scan_align
 
 
 def main():
@@ -31,6 +31,8 @@ def main():
             y = synth.letters(61, 3000); x = synth.letters(62, 20000); block = 512; exp = None
         elif cfg == "cfg2":
             y = synth.letters(2002, 16384); x = synth.letters(2001, 16384); block = 1024; exp = big["cfg2_random"]["score"]
+        elif cfg == "scan4":        # cfg4 through the row-parallel prefix-max scorer
+            y = synth.letters(4001, 2048); x = synth.letters(4002, 4194304); block = 4096; exp = big["cfg4"]["score"]
         elif cfg == "cfg4":
             y = synth.letters(4001, 2048); x = synth.letters(4002, 4194304); block = 16384; exp = big["cfg4"]["score"]
         else:
@@ -51,7 +53,10 @@ def main():
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            score = wave_align(eng, y, x, rank=rank, world=world, block_cols=block, epoch=epoch)
+            if cfg == "scan4":
+                score = scan_align(eng, y, x, rank=rank, world=world, epoch=epoch)
+            else:
+                score = wave_align(eng, y, x, rank=rank, world=world, block_cols=block, epoch=epoch)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             tt = torch.tensor([dt, eng.timing()["align_calc"] / 1e3], dtype=torch.float64, device="cuda")
