@@ -84,6 +84,7 @@ struct nwb200_ctx {
     bool trace_done = false;
     bool map_valid = false;          // the last fill launch also produced the origin maps
     bool fuse_map = true;
+    bool inline_map = false;
     bool edit_cached = false;
     std::string last_edit;
     unsigned last_hash = 0;

@@ -60,6 +60,8 @@ struct FillArgs {
     int* map;                // nullable (single block only): origin maps for the traceback, computed IN THIS LAUNCH by extra
                              // warps that follow the fill one band behind (map[b*ldr + kPadL + c], see nw_trace.cuh pass A)
     int negg;                // -gap (map units)
+    int map_inline;          // 0: map units shadow the fill units on otherwise idle SM sub-partitions (few bands);
+                             // 1: every band is swept ONCE with origin labels and publishes its header row itself (many bands)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p)
@@ -76,7 +78,7 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v)
 // Origin map of one band (traceback pass A, see nw_trace.cuh) computed inside the fill launch: the warp follows the
 // fill one band behind, consuming the same tagged header row the fill unit of this band consumes.
 template <int R, int K>
-__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const unsigned* sp_tab, const int b, const int lane)
+__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const unsigned* sp_tab, const int b, const int lane, const bool publish)
 {
     using SC = Sched<R, K>;
     constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
@@ -93,14 +95,16 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     }
     for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
     __syncwarp();
-    {
+    const bool consumer = b > 0;
+    unsigned long long* hr_out = a.HR + (long long)(b + 1) * a.ldr + kPadL;
+    if (consumer) {
         int c = 32 * (PD - 1 + a.slack) + 31;
         if (c > m - 1) c = m - 1;
         (void)wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
-    }
-    for (int g = 0; g < PD; g++) {
-        const int c = 32 * g + lane;
-        if (c < m) sm.rin[c & (VR - 1)] = wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
+        for (int g = 0; g < PD; g++) {
+            const int cc = 32 * g + lane;
+            if (cc < m) sm.rin[cc & (VR - 1)] = wait_tagged(hr_in + cc, ld_relaxed64(hr_in + cc), a.tag);
+        }
     }
     __syncwarp();
     Lane<R, 1> st;
@@ -116,7 +120,7 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     for (int lc = 0; lc < nlc; lc++) {
         const int cp = 32 * (lc + PD) + lane;
         unsigned long long pf_hr = 0;
-        const bool want_hr = cp < m;
+        const bool want_hr = consumer && cp < m;
         if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
         const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
         io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
@@ -124,12 +128,30 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
         io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
         io.map_out = map_row + (32 * lc - LAG);
         io.org0 = 32 * lc + 1;
+        io.rout_chunk = publish ? sm.rout + (lc & 1) * 32 : nullptr;
         sweep_chunk<R, K, 1>(st, lane, io, nullptr);
         __syncwarp();
+        if (publish && lc >= SC::GL) {
+            const int v = (lane >= SC::SH) ? sm.rout[(lc & 1) * 32 + lane - SC::SH] : sm.rout[((lc + 1) & 1) * 32 + 32 - SC::SH + lane];
+            st_relaxed64(hr_out + 32 * (lc - SC::GL) + lane, pack_tagged(v, a.tag));
+        }
         sm.rin[cp & (VR - 1)] = want_hr ? wait_tagged(hr_in + cp, pf_hr, a.tag) : 0;
         sm.put_letter(cp, pf_x);
+        if (publish && a.snap != nullptr && ((lc + 1) % a.snap_chunks) == 0) {
+            const int k = (lc + 1) / a.snap_chunks - 1;
+            if (k < a.nsnap) {
+                int* sp = a.snap + (((long long)b * a.nsnap + k) * 32 + lane) * SC::SNAP_INTS;
+#pragma unroll
+                for (int r = 0; r < R; r += 4)
+                    st_cs4(reinterpret_cast<int4*>(sp + r), make_int4(st.h[r], st.h[r + 1], st.h[r + 2], st.h[r + 3]));
+                st_cs4(reinterpret_cast<int4*>(sp + R), make_int4(st.dprev, st.up_next, 0, 0));
+            }
+        }
         __syncwarp();
     }
+    if (publish && lane < SC::SH)
+        st_relaxed64(hr_out + 32 * (nlc - SC::GL) + lane, pack_tagged(sm.rout[((nlc - 1) & 1) * 32 + 32 - SC::SH + lane], a.tag));
+    __syncwarp();
 }
 
 template <int R, int K, int WARPS>
@@ -144,7 +166,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int PD = a.pd;
     const bool with_map = a.map != nullptr;
-    const int nunits = with_map ? 2 * a.nb - 1 : a.nb * a.nq;
+    const bool inline_map = with_map && a.map_inline != 0;
+    const int nunits = inline_map ? a.nb : (with_map ? 2 * a.nb - 1 : a.nb * a.nq);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
     const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
 
@@ -153,8 +176,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         if (lane == 0) t = atomicAdd(a.ticket, 1);
         t = __shfl_sync(kFull, t, 0);
         if (t >= nunits) break;
+        if (inline_map) {                                     // one sweep per band: values, origin labels, header row, snapshots
+            map_unit<R, K>(a, sm, sp_tab, t, lane, true);
+            continue;
+        }
         if (with_map && t > 0 && (t & 1) == 0) {              // ticket 2k: origin map of band k (its input, header row k, comes from fill unit k-1)
-            map_unit<R, K>(a, sm, sp_tab, t >> 1, lane);
+            map_unit<R, K>(a, sm, sp_tab, t >> 1, lane, false);
             continue;
         }
         if (with_map) t = (t + 1) >> 1;                       // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...

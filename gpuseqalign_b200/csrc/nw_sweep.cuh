@@ -226,8 +226,12 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
                 const int b1 = max(cd, up);
                 const bool p2 = b1 < left;                // nwtrace1_plain.cpp:65: max < left -> move left
                 if constexpr (MODE == 1) {
+                    // the label coming down the column (oup) is the late input: everything else is selected first, so only
+                    // one SEL per row sits on the chain that runs down the lane's rows
                     const int oleft = st.o[r];
-                    const int on = p2 ? oleft : (p1 ? oup : odiag);
+                    const int early = p2 ? oleft : odiag;
+                    const bool take_up = p1 && !p2;
+                    const int on = take_up ? oup : early;
                     odiag = oleft; oup = on; st.o[r] = on;
                 } else {
                     const unsigned eqx = (xo[s] == yoff[r]) ? 0u : 1u;
@@ -241,6 +245,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];
         } else if constexpr (MODE == 1) {
             if (last) io.map_out[s] = st.o[R - 1];
+            if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];      // a map unit that is also the band's fill unit
         } else if constexpr (MODE == 2) {
             if constexpr (R == 4) io.dirs_lane[s * 32] = (unsigned char)codes;
             else if constexpr (R == 8) reinterpret_cast<unsigned short*>(io.dirs_lane)[s * 32] = (unsigned short)codes;

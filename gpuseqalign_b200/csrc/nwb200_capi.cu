@@ -79,7 +79,7 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     const Geometry& g = c->g;
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
-    long long ctas_needed = ((a.map ? 2LL * g.nb - 1 : (long long)g.nb * a.nq) + g.W - 1) / g.W;
+    long long ctas_needed = ((a.map ? (a.map_inline ? (long long)g.nb : 2LL * g.nb - 1) : (long long)g.nb * a.nq) + g.W - 1) / g.W;
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
@@ -254,7 +254,12 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     a.nb = g.nb; a.pad = g.pad;
     a.pd = 2; a.negg = -c->gap; a.map = nullptr;
     // the origin maps of the traceback ride along in the fill launch while every unit still gets an SM sub-partition of its own
-    if (keep && c->fuse_map && g.nb > 1 && 2LL * g.nb - 1 <= 4LL * c->sm_count) {
+    // Few bands: map units shadow the fill units on idle SM sub-partitions (one launch).  Many bands: the maps come from
+    // nw_map_kernel in nwb200_trace_resident; sweeping every band once WITH origin labels (map_inline) measured no better
+    // (200k x 200k: 45.6 ms vs 43.7 ms, profiles/), it stays available as a developer option.
+    const bool shadow = 2LL * g.nb - 1 <= 4LL * c->sm_count;
+    a.map_inline = (!shadow && c->inline_map) ? 1 : 0;
+    if (keep && c->fuse_map && g.nb > 1 && (shadow || a.map_inline)) {
         CU(c, c->d_map.ensure(sizeof(int) * (size_t)g.nb * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc maps");
         a.map = c->d_map.as<int>();
     }
@@ -338,7 +343,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
 {
     if (!c) return NWB200_ERR_INVALID_VALUE;
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
-    c->fuse_map = (enable & 4) == 0;
+    c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0;
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);
