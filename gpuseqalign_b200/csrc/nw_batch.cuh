@@ -78,13 +78,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         const int nlc = SC::nlc(m);
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
-            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : (unsigned)a.S;
-            if (pf_x > (unsigned)a.S) { pf_x = (unsigned)a.S; *a.err = 1; }
-            pf_x *= SC::LSTRIDE;
+            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : (unsigned)a.S;      // checked and scaled when it lands
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             sweep_chunk<R, K, 0, false>(st, lane, io, nullptr);
             __syncwarp();
-            sm.put_letter(cp, pf_x);
+            if (pf_x > (unsigned)a.S) { pf_x = (unsigned)a.S; *a.err = 1; }
+            sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }
         // lane 31's last row is row n of the matrix, frozen at column m: un-shift H = P + (n+m)*gap

@@ -117,12 +117,13 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     io.prof_lane = sm.prof + lane * 4 * SC::WPL;
     io.rout_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg; io.dump_lane = nullptr; io.dump_ld = 0;
     int* map_row = a.map + (long long)b * a.ldr + kPadL;
+    int snap_left = a.snap_chunks, snap_k = 0;
     for (int lc = 0; lc < nlc; lc++) {
         const int cp = 32 * (lc + PD) + lane;
         unsigned long long pf_hr = 0;
         const bool want_hr = consumer && cp < m;
         if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
-        const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+        const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) : (unsigned)a.S;
         io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
         io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
         io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
@@ -136,10 +137,11 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
             st_relaxed64(hr_out + 32 * (lc - SC::GL) + lane, pack_tagged(v, a.tag));
         }
         sm.rin[cp & (VR - 1)] = want_hr ? wait_tagged(hr_in + cp, pf_hr, a.tag) : 0;
-        sm.put_letter(cp, pf_x);
-        if (publish && a.snap != nullptr && ((lc + 1) % a.snap_chunks) == 0) {
-            const int k = (lc + 1) / a.snap_chunks - 1;
-            if (k < a.nsnap) {
+        sm.put_letter(cp, pf_x * SC::LSTRIDE);
+        if (--snap_left == 0) {
+            snap_left = a.snap_chunks;
+            const int k = snap_k++;
+            if (publish && a.snap != nullptr && k < a.nsnap) {
                 int* sp = a.snap + (((long long)b * a.nsnap + k) * 32 + lane) * SC::SNAP_INTS;
 #pragma unroll
                 for (int r = 0; r < R; r += 4)
@@ -248,13 +250,14 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
         io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0;
+        int snap_left = a.snap_chunks, snap_k = 0;
         for (int lc = 0; lc < nlc; lc++) {
             // ---- issue the prefetches of chunk lc + PD
             const int cp = 32 * (lc + PD) + lane;
             unsigned long long pf_hr = 0;
             const bool want_hr = consumer && cp < m;
             if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(xb + cp) * SC::LSTRIDE : ZOFF;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(xb + cp) : (unsigned)a.S;      // scaled when it lands: nothing waits on the load here
             // ---- the chunk itself
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
@@ -273,11 +276,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
                 else sm.rin[cp & (VR - 1)] = wait_tagged_count(hr_in + cp, pf_hr, a.tag, spins);
             }
             else if (consumer) sm.rin[cp & (VR - 1)] = 0;
-            sm.put_letter(cp, pf_x);
+            sm.put_letter(cp, pf_x * SC::LSTRIDE);
             // ---- snapshot of the register state for the traceback
-            if (a.snap != nullptr && ((lc + 1) % a.snap_chunks) == 0) {
-                const int k = (lc + 1) / a.snap_chunks - 1;
-                if (k < a.nsnap) {
+            if (--snap_left == 0) {
+                snap_left = a.snap_chunks;
+                const int k = snap_k++;
+                if (a.snap != nullptr && k < a.nsnap) {
                     int* sp = a.snap + (((long long)b * a.nsnap + k) * 32 + lane) * SC::SNAP_INTS;
 #pragma unroll
                     for (int r = 0; r < R; r += 4)

@@ -173,38 +173,64 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
     constexpr int WPL = SC::WPL;
     const int src_lane = (lane + 31) & 31;
     const bool last = (lane == 31);
-    // software pipeline: letter offsets 3 steps ahead, profile words 2 steps ahead, top row 2 steps ahead
-    unsigned xo[32 + 3];
+    // A single warp can issue a shared-memory / shuffle instruction only every ~5-6 clk (measured: LDS.32 20 thread-ops/clk/SM
+    // at one warp per SM sub-partition, profiles/microbench_r1.jsonl), and that -- not the DPX chain -- bounds the step of a
+    // lone warp.  So the loads are widened: letter offsets two steps per LDS.32 (K == 2: the lane's ring position is even),
+    // the top row four steps per LDS.128, and lane 31's bottom row / map row leave four (two) steps per store.
+    // software pipeline: letter offsets >= 3 steps ahead, profile words 2 steps ahead, top row >= 2 steps ahead
+    unsigned xo[32 + 4];
     unsigned pw[32 + 2][WPL];
-    int rv[32 + 2];
+    int rv[32 + 8];
+    int outv[32];      // lane 31's bottom-row values of this chunk (registers; stored four at a time)
+    int outo[32];      // MODE 1: their origin labels
     auto load_pw = [&](int s) {
         const unsigned char* pp = io.prof_lane + xo[s];
         if constexpr (WPL == 1) pw[s][0] = *reinterpret_cast<const unsigned*>(pp);
         else if constexpr (WPL == 2) { uint2 v = *reinterpret_cast<const uint2*>(pp); pw[s][0] = v.x; pw[s][1] = v.y; }
         else { uint4 v = *reinterpret_cast<const uint4*>(pp); pw[s][0] = v.x; pw[s][1] = v.y; pw[s][2] = v.z; pw[s][3] = v.w; }
     };
-    auto load_rv = [&](int s) {      // rv[s] = top-row value handed to lane 0 by the shuffle issued at step s
-        constexpr int A = (K == 2) ? 1 : 0;
-        if constexpr (TOP) rv[s] = (s + A < 32) ? io.rin_chunk[s + A] : io.rin_next[0];
-        else rv[s] = 0;                                   // row 0 of P above the band: no top-row ring at all
+    auto load_xo = [&](int s) {      // fills xo[s] (and xo[s+1] when the ring position allows a paired load)
+        if constexpr (K == 2) {
+            if ((s & 1) == 0 && s < 32) {
+                const unsigned v = *reinterpret_cast<const unsigned*>(io.xs_lane + s);
+                xo[s] = v & 0xffffu; xo[s + 1] = v >> 16;
+            }
+        } else {
+            if (s < 32) xo[s] = io.xs_lane[s];
+        }
     };
+    // rvq[s]: top-row element s of this chunk's group (element 32 = first element of the next group)
+    auto load_rv4 = [&](int q) {     // elements 4q .. 4q+3
+        if constexpr (TOP) {
+            if (q < 8) {
+                const int4 v = *reinterpret_cast<const int4*>(io.rin_chunk + 4 * q);
+                rv[4 * q] = v.x; rv[4 * q + 1] = v.y; rv[4 * q + 2] = v.z; rv[4 * q + 3] = v.w;
+            } else {
+                rv[32] = io.rin_next[0];
+            }
+        }
+    };
+    constexpr int A = (K == 2) ? 1 : 0;          // the shuffle issued at step s carries top-row element s + A
 #pragma unroll
-    for (int s = 0; s < 3; s++) xo[s] = io.xs_lane[s];
+    for (int s = 0; s < 4; s++) load_xo(s);
+    load_rv4(0); load_rv4(1);
 #pragma unroll
-    for (int s = 0; s < 2; s++) { load_pw(s); load_rv(s); }
+    for (int s = 0; s < 2; s++) load_pw(s);
 #pragma unroll
     for (int s = 0; s < 32; s++) {
-        if (s + 3 < 32) xo[s + 3] = io.xs_lane[s + 3];
-        if (s + 2 < 32) { load_pw(s + 2); load_rv(s + 2); }
+        if constexpr (K == 2) { if ((s & 1) == 0) load_xo(s + 4); } else { load_xo(s + 3); }
+        if ((s & 3) == 0) load_rv4(s / 4 + 2);
+        if (s + 2 < 32) load_pw(s + 2);
+        const int rvs = TOP ? rv[s + A] : 0;
         // Rotate-shuffle: lanes 0..30 hand their bottom row to the lane below; lane 31 hands lane 0 its next
         // input from the row above the band, so the result feeds the first VIMNMX3 directly.
         int up, oup = 0;
         if constexpr (K == 1) {
-            up = __shfl_sync(kFull, last ? rv[s] : st.h[R - 1], src_lane);
+            up = __shfl_sync(kFull, last ? rvs : st.h[R - 1], src_lane);
             if constexpr (MODE == 1) oup = __shfl_sync(kFull, last ? io.org0 + s : st.o[R - 1], src_lane);
         } else {
             up = st.up_next;
-            st.up_next = __shfl_sync(kFull, last ? rv[s] : st.h[R - 1], src_lane);     // consumed at step s+1
+            st.up_next = __shfl_sync(kFull, last ? rvs : st.h[R - 1], src_lane);     // consumed at step s+1
             if constexpr (MODE == 1) {
                 oup = st.oup_next;
                 st.oup_next = __shfl_sync(kFull, last ? io.org0 + s + 1 : st.o[R - 1], src_lane);
@@ -241,11 +267,16 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             }
             diag = left; up = nv; st.h[r] = nv;
         }
-        if constexpr (MODE == 0) {
-            if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];
-        } else if constexpr (MODE == 1) {
-            if (last) io.map_out[s] = st.o[R - 1];
-            if (io.rout_chunk != nullptr && last) io.rout_chunk[s] = st.h[R - 1];      // a map unit that is also the band's fill unit
+        if constexpr (MODE == 0 || MODE == 1) {
+            outv[s] = st.h[R - 1];
+            if ((s & 3) == 3 && io.rout_chunk != nullptr && last)
+                *reinterpret_cast<int4*>(io.rout_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+        }
+        if constexpr (MODE == 1) {
+            outo[s] = st.o[R - 1];
+            // map_out + s is 8-byte aligned for even s (the row starts at an even element: kPadL, 32*lc and LAG are even for K == 2)
+            if constexpr (K == 2) { if ((s & 1) == 1 && last) *reinterpret_cast<int2*>(io.map_out + s - 1) = make_int2(outo[s - 1], outo[s]); }
+            else { if (last) io.map_out[s] = outo[s]; }
         } else if constexpr (MODE == 2) {
             if constexpr (R == 4) io.dirs_lane[s * 32] = (unsigned char)codes;
             else if constexpr (R == 8) reinterpret_cast<unsigned short*>(io.dirs_lane)[s * 32] = (unsigned short)codes;

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) : (unsigned)a.S;      // scaled when it lands
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
             io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
             sweep_chunk<R, K, 1>(st, lane, io, nullptr);
             __syncwarp();
             sm.rin[cp & (VR - 1)] = pf_top;
-            sm.put_letter(cp, pf_x);
+            sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }
     }
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
         for (int lc = lc0; lc <= lc_hi; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) : (unsigned)a.S;      // scaled when it lands
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
             io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
             sweep_chunk<R, K, 2>(st, lane, io, yoff);
             __syncwarp();
             sm.rin[cp & (VR - 1)] = pf_top;
-            sm.put_letter(cp, pf_x);
+            sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }
         // ---- walk the window (uniform across the warp; lane 0 stores)
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
-            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) * SC::LSTRIDE : ZOFF;
+            const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) : (unsigned)a.S;      // scaled when it lands
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
             io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
             sweep_chunk<R, K, 3>(st, lane, io, nullptr);
             __syncwarp();
             sm.rin[cp & (VR - 1)] = pf_top;
-            sm.put_letter(cp, pf_x);
+            sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }
     }
