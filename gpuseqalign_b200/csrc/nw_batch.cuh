@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     ChunkIO io;
     io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-    io.rin_chunk = nullptr; io.rin_next = nullptr; io.rout_chunk = nullptr; io.map_out = nullptr; io.org0 = 0;
+    io.rin_chunk = nullptr; io.rin_next = nullptr; io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.map_out = nullptr; io.org0 = 0;
     io.dirs_lane = nullptr; io.negg = 0;
 
     for (;;) {

@@ -64,13 +64,20 @@ __device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned lon
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Set when a wait for a tagged element gave up (a producer that never publishes must not hang the GPU): the host
+// reports errorInvalidResult.  ~2^21 polls of >= 20 ns + an L2 round trip each are several seconds.
+__device__ int g_wait_timeout = 0;
+constexpr unsigned kMaxPolls = 1u << 21;
+
 // returns the value once its tag matches; `first` is an earlier (prefetched) read of *p
 __device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned long long first, unsigned tag)
 {
     unsigned long long v = first;
+    unsigned polls = 0;
     while ((unsigned)(v >> 32) != tag) {
         __nanosleep(20);
         v = ld_relaxed64(p);
+        if (++polls > kMaxPolls) { g_wait_timeout = 1; break; }
     }
     return (int)(unsigned)v;
 }
@@ -78,10 +85,12 @@ __device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned
 __device__ __forceinline__ int wait_tagged_count(const unsigned long long* p, unsigned long long first, unsigned tag, unsigned& spins)
 {
     unsigned long long v = first;
+    unsigned polls = 0;
     while ((unsigned)(v >> 32) != tag) {
         __nanosleep(20);
         v = ld_relaxed64(p);
         spins++;
+        if (++polls > kMaxPolls) { g_wait_timeout = 1; break; }
     }
     return (int)(unsigned)v;
 }

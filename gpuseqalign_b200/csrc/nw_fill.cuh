@@ -60,6 +60,10 @@ struct FillArgs {
     int* map;                // nullable (single block only): origin maps for the traceback, computed IN THIS LAUNCH by extra
                              // warps that follow the fill one band behind (map[b*ldr + kPadL + c], see nw_trace.cuh pass A)
     int negg;                // -gap (map units)
+    unsigned long long* MID; // nullable: MID[b*ldr + kPadL + c] = (tag << 32 | P[middle row of band b][c+1]) -- the bottom row of lane 15,
+                             // published like HR so that the map units can work on HALF bands (two rows per lane: the step of a
+                             // map unit then costs what a fill step costs and the maps finish right behind the fill)
+    int map_half;            // 1: map[(2b+h)*ldr + ...] is the map of half h (0 upper, 1 lower) of band b; 0: map[b*ldr + ...] whole bands
     int map_inline;          // 0: map units shadow the fill units on otherwise idle SM sub-partitions (few bands);
                              // 1: every band is swept ONCE with origin labels and publishes its header row itself (many bands)
 };
@@ -75,19 +79,23 @@ __device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v)
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Origin map of one band (traceback pass A, see nw_trace.cuh) computed inside the fill launch: the warp follows the
-// fill one band behind, consuming the same tagged header row the fill unit of this band consumes.
+// Origin map of one band or half band (traceback pass A, see nw_trace.cuh) computed inside the fill launch: the warp
+// follows the fill, consuming the same tagged rows the fill publishes.  `hr_in` = the row above the unit's rows (nullptr:
+// row 0 of the matrix), `prow_base` = padded index of its first row, `map_row` = where lane 31's labels go,
+// `b_out` = band whose header row / snapshots this unit publishes itself (publish only: the unit then IS the band's fill).
 template <int R, int K>
-__device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, const unsigned* sp_tab, const int b, const int lane, const bool publish)
+__device__ __forceinline__ void map_unit(const FillArgs& a, unsigned char* warp_smem, const unsigned* sp_tab, const unsigned long long* hr_in,
+                                         const long long prow_base, int* map_row, const int b_out, const int lane, const bool publish)
 {
     using SC = Sched<R, K>;
-    constexpr int By = SC::By, LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
+    constexpr int LAG = SC::LAG, VR = SC::VR, XR = SC::XR;
+    WarpSmem<R, K> sm(warp_smem, a.S);
+    const int b = b_out;
     const int PD = a.pd;
     const int m = a.m, nlc = SC::nlc(m);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
-    const long long prow0 = (long long)b * By + (long long)lane * R;
+    const long long prow0 = prow_base + (long long)lane * R;
     build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
-    const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
     for (int c = -64 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
     for (int g = 0; g < PD; g++) {
         const int c = 32 * g + lane;
@@ -95,7 +103,7 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     }
     for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
     __syncwarp();
-    const bool consumer = b > 0;
+    const bool consumer = hr_in != nullptr;
     unsigned long long* hr_out = a.HR + (long long)(b + 1) * a.ldr + kPadL;
     if (consumer) {
         int c = 32 * (PD - 1 + a.slack) + 31;
@@ -115,8 +123,7 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, WarpSmem<R, K>& sm, 
     st.oup_next = (lane == 0) ? 1 : 0;
     ChunkIO io;
     io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-    io.rout_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg; io.dump_lane = nullptr; io.dump_ld = 0;
-    int* map_row = a.map + (long long)b * a.ldr + kPadL;
+    io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg; io.dump_lane = nullptr; io.dump_ld = 0;
     int snap_left = a.snap_chunks, snap_k = 0;
     for (int lc = 0; lc < nlc; lc++) {
         const int cp = 32 * (lc + PD) + lane;
@@ -169,9 +176,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
     const int PD = a.pd;
     const bool with_map = a.map != nullptr;
     const bool inline_map = with_map && a.map_inline != 0;
-    const int nunits = inline_map ? a.nb : (with_map ? 2 * a.nb - 1 : a.nb * a.nq);
+    const bool half_map = with_map && !inline_map && a.map_half != 0;
+    // units: fill units only | band 0 fill + (fill, map) per further band | band 0 fill + (fill, upper map, lower map) per further band
+    const int nunits = inline_map ? a.nb : (with_map ? (half_map ? 3 * a.nb - 2 : 2 * a.nb - 1) : a.nb * a.nq);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
     const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
+    unsigned char* warp_smem = smem_raw + (size_t)w * SC::warp_smem_bytes(a.S);
 
     for (;;) {
         int t = 0;
@@ -179,14 +189,34 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         t = __shfl_sync(kFull, t, 0);
         if (t >= nunits) break;
         if (inline_map) {                                     // one sweep per band: values, origin labels, header row, snapshots
-            map_unit<R, K>(a, sm, sp_tab, t, lane, true);
+            map_unit<R, K>(a, warp_smem, sp_tab, t > 0 ? a.HR + (long long)t * a.ldr + kPadL : nullptr, (long long)t * By,
+                           a.map + (long long)t * a.ldr + kPadL, t, lane, true);
             continue;
         }
-        if (with_map && t > 0 && (t & 1) == 0) {              // ticket 2k: origin map of band k (its input, header row k, comes from fill unit k-1)
-            map_unit<R, K>(a, sm, sp_tab, t >> 1, lane, false);
-            continue;
+        if (half_map && t > 0) {
+            // ticket 1 + 3(b-1) + k: k = 0 fill of band b, k = 1 map of its upper half (input: header row b, from fill b-1),
+            // k = 2 map of its lower half (input: the middle row that fill b publishes)
+            const int bb = 1 + (t - 1) / 3, k = (t - 1) % 3;
+            if (k == 1) {
+                map_unit<R / 2, K>(a, warp_smem, sp_tab, a.HR + (long long)bb * a.ldr + kPadL, (long long)bb * By,
+                               a.map + (long long)(2 * bb) * a.ldr + kPadL, bb, lane, false);
+                continue;
+            }
+            if (k == 2) {
+                map_unit<R / 2, K>(a, warp_smem, sp_tab, a.MID + (long long)bb * a.ldr + kPadL, (long long)bb * By + By / 2,
+                               a.map + (long long)(2 * bb + 1) * a.ldr + kPadL, bb, lane, false);
+                continue;
+            }
+            t = bb;
+        } else if (with_map && t > 0) {
+            if ((t & 1) == 0) {                               // ticket 2k: origin map of band k (its input, header row k, comes from fill unit k-1)
+                const int bb = t >> 1;
+                map_unit<R, K>(a, warp_smem, sp_tab, a.HR + (long long)bb * a.ldr + kPadL, (long long)bb * By,
+                               a.map + (long long)bb * a.ldr + kPadL, bb, lane, false);
+                continue;
+            }
+            t = (t + 1) >> 1;                                 // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
         }
-        if (with_map) t = (t + 1) >> 1;                       // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
         const int q = t / a.nb, b = t - q * a.nb;             // tickets run block-major: (q, b-1) is always taken before (q, b)
         const int gb = q * a.world + a.rank;                  // global column block
         const long long c0 = (long long)gb * a.wc;            // its first column
@@ -230,6 +260,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         const bool consumer = (b > 0);                 // band 0 has row 0 (P = 0) above it
         const unsigned long long* hr_in = a.HR + (long long)q * a.hr_stride + (long long)b * a.ldr + kPadL;
         unsigned long long* hr_out = a.HR + (long long)q * a.hr_stride + (long long)(b + 1) * a.ldr + kPadL;
+        unsigned long long* mid_out = (half_map && b > 0) ? a.MID + (long long)b * a.ldr + kPadL : nullptr;
+        constexpr int GLM = (15 * K + 31) / 32, SHM = 32 * GLM - 15 * K;
         __syncwarp();
         // ---- prologue: the first PD groups of the row above
         if (consumer) {
@@ -249,7 +281,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
 
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0;
+        io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0; io.rmid_chunk = nullptr;
         int snap_left = a.snap_chunks, snap_k = 0;
         for (int lc = 0; lc < nlc; lc++) {
             // ---- issue the prefetches of chunk lc + PD
@@ -263,12 +295,18 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
             io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
             io.rout_chunk = sm.rout + (lc & 1) * 32;
+            io.rmid_chunk = mid_out != nullptr ? sm.rmid + (lc & 1) * 32 : nullptr;
             sweep_chunk<R, K, 0>(st, lane, io, nullptr);
             __syncwarp();
             // ---- publish the group of the bottom row that this chunk completed: ONE coalesced 256-byte store
             if (lc >= SC::GL) {
                 const int v = (lane >= SC::SH) ? sm.rout[(lc & 1) * 32 + lane - SC::SH] : sm.rout[((lc + 1) & 1) * 32 + 32 - SC::SH + lane];
                 st_relaxed64(hr_out + 32 * (lc - SC::GL) + lane, pack_tagged(v, a.tag));
+            }
+            // ---- and the group of the middle row (lane 15 is 15*K columns behind lane 0)
+            if (mid_out != nullptr && lc >= GLM) {
+                const int v = (lane >= SHM) ? sm.rmid[(lc & 1) * 32 + lane - SHM] : sm.rmid[((lc + 1) & 1) * 32 + 32 - SHM + lane];
+                st_relaxed64(mid_out + 32 * (lc - GLM) + lane, pack_tagged(v, a.tag));
             }
             // ---- land the prefetches
             if (want_hr) {
@@ -293,6 +331,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         }
         // ---- the first SH elements of the next group were produced by the last chunk (they hold the last real column)
         if (lane < SC::SH) st_relaxed64(hr_out + 32 * (nlc - SC::GL) + lane, pack_tagged(sm.rout[((nlc - 1) & 1) * 32 + 32 - SC::SH + lane], a.tag));
+        if (mid_out != nullptr && lane < SHM)
+            st_relaxed64(mid_out + 32 * (nlc - GLM) + lane, pack_tagged(sm.rmid[((nlc - 1) & 1) * 32 + 32 - SHM + lane], a.tag));
         if (a.dbg && lane == 0 && q == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
         // ---- every row is frozen at its last-column value by now
         if (has_right) {

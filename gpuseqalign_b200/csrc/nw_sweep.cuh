@@ -39,9 +39,9 @@ constexpr int kPadL = 64;     // elements of padding in front of every header ro
 
 template <int R, int K>
 struct Sched {
-    static_assert(R == 4 || R == 8 || R == 16, "rows per lane");
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "rows per lane");
     static_assert(K == 1 || K == 2, "lane skew");
-    static constexpr int WPL = R / 4;                  // profile words per lane and letter
+    static constexpr int WPL = (R + 3) / 4;            // profile words per lane and letter (R == 2 uses half a word)
     static constexpr int By = 32 * R;                  // rows per band
     static constexpr int LAG = 31 * K;                 // columns lane 31 is behind lane 0
     static constexpr int PD = 2;                       // top-row / letter groups prefetched ahead
@@ -57,7 +57,7 @@ struct Sched {
     __host__ __device__ static constexpr size_t prof_bytes(int S) { return (size_t)(S + 1) * LSTRIDE; }
     __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
     {
-        return (prof_bytes(S) + (size_t)VR * 4 + 64 * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
+        return (prof_bytes(S) + (size_t)VR * 4 + 128 * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
     }
 };
 
@@ -79,13 +79,15 @@ struct WarpSmem {
     unsigned char* prof;     // [(S+1)][32 lanes][WPL] words: bytes s'(y[row r], letter)
     int* rin;                // [VR] top-row ring: P[top][c] at (c & (VR-1))
     int* rout;               // [64] bottom-row staging: chunk lc, step s at ((lc & 1) * 32 + s)
+    int* rmid;               // [64] the same for the band's MIDDLE row (bottom row of lane 15), see nw_fill.cuh
     unsigned short* xs;      // [XR + XM] letter ring: profile byte offset (letter * LSTRIDE) of column c at (c & (XR-1))
     __device__ __forceinline__ WarpSmem(unsigned char* base, int S)
     {
         prof = base;
         rin = reinterpret_cast<int*>(base + SC::prof_bytes(S));
         rout = rin + SC::VR;
-        xs = reinterpret_cast<unsigned short*>(rout + 64);
+        rmid = rout + 64;
+        xs = reinterpret_cast<unsigned short*>(rmid + 64);
     }
     __device__ __forceinline__ void put_letter(int c, unsigned off16)
     {
@@ -131,7 +133,7 @@ __device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const un
         const unsigned* row[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const unsigned yy = yl[q * 4 + r];
+            const unsigned yy = (q * 4 + r < R) ? yl[(q * 4 + r < R) ? q * 4 + r : 0] : 0xffu;
             row[r] = sp_tab + (yy != 0xffu && yy < (unsigned)S ? yy : (unsigned)S) * kSpPitch;
         }
         for (int g4 = 0; 4 * g4 < S; g4++) {
@@ -157,6 +159,7 @@ struct ChunkIO {
     const int* rin_chunk;            // &rin[(32*lc) & (VR-1)]: top row for lane 0, index s
     const int* rin_next;             // &rin[(32*lc + 32) & (VR-1)]: first element of the next group (K == 2 look-ahead)
     int* rout_chunk;                 // MODE 0: &rout[(lc & 1) * 32] (lane 31 stores element s), nullptr = keep nothing
+    int* rmid_chunk;                 // MODE 0: &rmid[(lc & 1) * 32] (lane 15 stores element s), nullptr = keep nothing
     int* map_out;                    // MODE 1: &map[32*lc - LAG] (lane 31 stores element s)
     int org0;                        // MODE 1: label of the cell above lane 0 at step 0 of this chunk (= 32*lc + 1)
     unsigned char* dirs_lane;        // MODE 2: &dirs[(32*(lc-lc0))*32 + lane], one byte (R=4) / two (R=8) / four (R=16) per step
@@ -271,6 +274,10 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             outv[s] = st.h[R - 1];
             if ((s & 3) == 3 && io.rout_chunk != nullptr && last)
                 *reinterpret_cast<int4*>(io.rout_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+            if constexpr (MODE == 0) {
+                if ((s & 3) == 3 && io.rmid_chunk != nullptr && lane == 15)
+                    *reinterpret_cast<int4*>(io.rmid_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+            }
         }
         if constexpr (MODE == 1) {
             outo[s] = st.o[R - 1];

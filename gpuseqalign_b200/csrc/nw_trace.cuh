@@ -42,6 +42,7 @@ struct TraceArgs {
     unsigned char* ops;              // per-band move lists, codes 0 '=', 1 'X', 2 'I', 3 'D'
     unsigned char* dense;            // packed backward move list
     long long* total;                // [2]: total moves, consistency flag
+    int map_half;                    // 1: map rows 2b (upper half of band b) and 2b+1 (lower half); 0: one map row per band
 };
 
 // Loads a plain (already complete) header-row group into the top-row ring.
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
         st.oup_next = (lane == 0) ? 1 : 0;
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.rout_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg;
+        io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg;
         int* map_row = a.map + (long long)b * a.ldr + kPadL;
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
@@ -121,7 +122,14 @@ __global__ void nw_hop_kernel(const TraceArgs a, int By)
     for (int b = a.nb - 1; b >= 0; b--) {
         a.entry[b] = j;
         int jn = 0;
-        if (b > 0 && j > 0) jn = a.map[(long long)b * a.ldr + kPadL + (j - 1)];
+        if (b > 0 && j > 0) {
+            if (a.map_half) {                         // through the lower half to the band's middle row, then through the upper half
+                const int jm = a.map[(long long)(2 * b + 1) * a.ldr + kPadL + (j - 1)];
+                jn = jm > 0 ? a.map[(long long)(2 * b) * a.ldr + kPadL + (jm - 1)] : 0;
+            } else {
+                jn = a.map[(long long)b * a.ldr + kPadL + (j - 1)];
+            }
+        }
         a.off[b] = off;
         off += (long long)By + (j - jn) + 4;
         j = jn;
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
         }
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.rout_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.negg = a.negg;
+        io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.negg = a.negg;
         for (int lc = lc0; lc <= lc_hi; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (hr_in != nullptr && cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
@@ -332,7 +340,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
         st.up_next = (lane == 0) ? sm.rin[0] : 0;
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-        io.rout_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
+        io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0;
         io.dump_ld = a.ld;
         int* slab_lane = a.slab + ((long long)bi * By + (long long)lane * R) * a.ld + kPadL - K * lane;
         for (int lc = 0; lc < nlc; lc++) {

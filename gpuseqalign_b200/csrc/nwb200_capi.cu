@@ -42,8 +42,8 @@ int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
         if (p->reserved) K = p->reserved;
     }
     if (R == 0) R = ((long long)n <= 4LL * 32 * 4 * c->sm_count) ? 4 : 8;      // one warp per SM sub-partition while that covers all rows
-    if (!(R == 4 || R == 8 || R == 16) || !(W == 1 || W == 2 || W == 4 || W == 8) || Bx < 32 || (Bx % 32) != 0 || Bx > (R == 16 ? 512 : 1024) || !(K == 1 || K == 2))
-        return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8,16}, warps_per_block in {1,2,4,8}, tile_cols multiple of 32 up to 1024, skew in {1,2})");
+    if (!(R == 4 || R == 8 || R == 16) || !(W == 1 || W == 4) || Bx < 32 || (Bx % 32) != 0 || Bx > (R == 16 ? 512 : 1024) || !(K == 1 || K == 2))
+        return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8,16}, warps_per_block in {1,4}, tile_cols multiple of 32 up to 1024, skew in {1,2})");
     const int By = R * 32;
     long long nb = ((long long)n + By - 1) / By;
     if (nb < 1) nb = 1;
@@ -79,13 +79,13 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     const Geometry& g = c->g;
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
-    long long ctas_needed = ((a.map ? (a.map_inline ? (long long)g.nb : 2LL * g.nb - 1) : (long long)g.nb * a.nq) + g.W - 1) / g.W;
+    long long ctas_needed = ((a.map ? (a.map_inline ? (long long)g.nb : (a.map_half ? 3LL * g.nb - 2 : 2LL * g.nb - 1)) : (long long)g.nb * a.nq) + g.W - 1) / g.W;
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
 #define NWB_CASE(R_, K_, W_) if (g.R == R_ && g.K == K_ && g.W == W_) return launch_fill_t<R_, K_, W_>(c, a, (int)grid)
     NWB_CASE(4, 2, 4); NWB_CASE(4, 1, 4); NWB_CASE(8, 2, 4); NWB_CASE(8, 1, 4); NWB_CASE(16, 2, 4); NWB_CASE(16, 1, 4);
-    NWB_CASE(4, 2, 1); NWB_CASE(4, 2, 2); NWB_CASE(4, 2, 8); NWB_CASE(8, 2, 1); NWB_CASE(8, 2, 2); NWB_CASE(8, 2, 8);
+    NWB_CASE(4, 2, 1); NWB_CASE(8, 2, 1);
 #undef NWB_CASE
     return fail(c, NWB200_ERR_INVALID_VALUE, "no kernel instance for these tile parameters");
 }
@@ -124,7 +124,7 @@ void nwb200_destroy(nwb200_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
-                      &c->d_map, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2,
+                      &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2,
                       &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_dbg, &c->d_wave})
         b->release();
     c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release(); c->h_export.release();
@@ -259,11 +259,20 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     // (200k x 200k: 45.6 ms vs 43.7 ms, profiles/), it stays available as a developer option.
     const bool shadow = 2LL * g.nb - 1 <= 4LL * c->sm_count;
     a.map_inline = (!shadow && c->inline_map) ? 1 : 0;
+    // half-band map units (two rows per lane) keep pace with the fill units; they need one SM sub-partition each as well
+    const bool half = shadow && !a.map_inline && c->half_map && 3LL * g.nb - 2 <= 4LL * c->sm_count;
+    a.map_half = half ? 1 : 0; a.MID = nullptr;
     if (keep && c->fuse_map && g.nb > 1 && (shadow || a.map_inline)) {
-        CU(c, c->d_map.ensure(sizeof(int) * (size_t)g.nb * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc maps");
+        CU(c, c->d_map.ensure(sizeof(int) * (size_t)(half ? 2 : 1) * (size_t)g.nb * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc maps");
         a.map = c->d_map.as<int>();
+        if (half) {
+            const size_t before = c->d_MID.cap;
+            CU(c, c->d_MID.ensure(sizeof(unsigned long long) * (size_t)g.nb * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc middle rows");
+            if (c->d_MID.cap != before) CU(c, cudaMemsetAsync(c->d_MID.p, 0, c->d_MID.cap, c->stream), NWB200_ERR_CUDA_GENERAL, "memset middle rows");
+            a.MID = c->d_MID.as<unsigned long long>();
+        }
     }
-    c->map_valid = a.map != nullptr;
+    c->map_valid = a.map != nullptr; c->map_is_half = a.map != nullptr && half;
     a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
     if (c->dbg_stamps) {
         CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
@@ -289,6 +298,15 @@ int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
     CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel execution", e);
+    {
+        int timed_out = 0;
+        cudaMemcpyFromSymbol(&timed_out, g_wait_timeout, sizeof(int));
+        if (timed_out) {
+            int zero = 0;
+            cudaMemcpyToSymbol(g_wait_timeout, &zero, sizeof(int));
+            return fail(c, NWB200_ERR_INVALID_RESULT, "a band waited too long for its header row (producer never published)");
+        }
+    }
     if ((unsigned)(hs[0] >> 32) != c->epoch) return fail(c, NWB200_ERR_INVALID_RESULT, "the fill did not publish the score element");
     // un-shift: H[n][m] = P[n][m] + (n+m)*gap
     *align_cost = (int32_t)((long long)(int)(unsigned)hs[0] + ((long long)g.n + g.m) * c->gap);
@@ -343,7 +361,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
 {
     if (!c) return NWB200_ERR_INVALID_VALUE;
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
-    c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0;
+    c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0;
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);

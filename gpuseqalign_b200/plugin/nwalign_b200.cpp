@@ -11,7 +11,7 @@
 // nw.subst / nw.substsz / nw.gapoCost; outputs are res.align_cost, res.edit_trace, res.trace_hash, res.score_hash,
 // the Stopwatch laps with the TSV column names (file_formats.cpp:505-518), res.cudaStat on CUDA failure; every
 // failure is an NwStat, nothing throws.  Parameters (all optional in the param JSON, 0 = engine default):
-//     "rowsPerLane" (4, 8, 16), "warpsPerBlock" (1, 2, 4, 8), "tileCols" (snapshot spacing, multiple of 32), "skew" (1, 2).
+//     "rowsPerLane" (4, 8, 16), "warpsPerBlock" (1, 4), "tileCols" (snapshot spacing, multiple of 32), "skew" (1, 2).
 #include "nw_algorithm.hpp"
 #include "nw_fns.hpp"
 #include "nwalign_shared.hpp"

@@ -56,13 +56,13 @@ typedef struct nwb200_ctx nwb200_ctx;
 
 /* Tile geometry: the analogue of the reference's per-algorithm parameters
  * (param_best.json: subtileRows/subtileCols/subtileBx for gpu9; nwalign_gpu9...cu:384-398).
- * tile_rows is fixed by the kernel shape (rows per lane x 32 lanes x warps per block);
- * tile_cols is the header-column spacing, a multiple of 32.  0 = engine default. */
+ * tile_rows is fixed by the kernel shape (rows per lane x 32 lanes); tile_cols is the spacing of the
+ * register snapshots that play the role of the reference's header columns.  0 = engine default. */
 typedef struct nwb200_params {
-    int32_t rows_per_lane;   /* 4 (default) or 8 */
-    int32_t warps_per_block; /* 1..8, default 4   */
-    int32_t tile_cols;       /* header column spacing Bx, multiple of 32, default 512 */
-    int32_t reserved;
+    int32_t rows_per_lane;   /* 4, 8 or 16: rows per lane, band height = 32 x this (0: 4 up to 75 776 rows, else 8) */
+    int32_t warps_per_block; /* 1 or 4 warps per CTA of the fill launch (0: 4)                                       */
+    int32_t tile_cols;       /* snapshot spacing Bx in columns, multiple of 32, <= 1024 (0: 512)                      */
+    int32_t reserved;        /* lane skew K: 1 or 2 (0: 2)                                                            */
 } nwb200_params;
 
 /* Flags for nwb200_align_pair_*. */

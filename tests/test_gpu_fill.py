@@ -43,7 +43,7 @@ def test_golden_traces(engine, golden):
 
 
 VARIANTS = [(4, 4, 2, 512), (4, 4, 1, 512), (8, 4, 2, 256), (8, 4, 1, 96), (16, 4, 2, 32), (16, 4, 1, 512),
-            (4, 1, 2, 64), (4, 2, 2, 1024), (4, 8, 2, 128), (8, 1, 2, 512), (8, 2, 2, 64), (8, 8, 2, 1024)]
+            (4, 1, 2, 64), (8, 1, 2, 1024), (4, 4, 2, 1024), (8, 4, 2, 64)]
 
 
 @pytest.mark.parametrize("R,W,K,Bx", VARIANTS)
@@ -148,7 +148,7 @@ def test_score_hash_multi_band_and_variants(engine, scoring, oracle):
     subst = scoring["subst"]["blosum62"]
     x = synth.letters(31, 1900); y = synth.letters(32, 1333)
     exp = oracle.align_pair(y, x, subst, -11, want_hash=True, want_trace=False)
-    for p in (None, Params(8, 4, 256, 1), Params(16, 4, 64, 2), Params(4, 2, 32, 2)):
+    for p in (None, Params(8, 4, 256, 1), Params(16, 4, 64, 2), Params(4, 1, 32, 2)):
         assert engine.align(y, x, keep_headers=True, params=p) == exp.score
         assert engine.score_hash() == exp.score_hash
 
