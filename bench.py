@@ -99,6 +99,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
 
 
+def pair_config(n, m, with_trace=True):
+    return {"workload": f"cfg2: single synthetic protein pair {n}x{m} per GPU, score" + ("+traceback" if with_trace else " only"),
+            "pairs_per_gpu": 1, "seeds": "X 2001+10r, Y 2002+10r (splitmix64, independent)", "subst": "blosum62", "gap": -11,
+            "l2": "flushed between timed steps (256 MiB memset)"}
+
+
+def batch_config(total_pairs, per):
+    return {"workload": f"cfg3: batch of {total_pairs} synthetic 256x256 pairs, scores only, sharded {per}/GPU",
+            "pairs_per_gpu": per, "seeds": "pair p: X 3e6+2p, Y 3e6+2p+1", "subst": "blosum62", "gap": -11,
+            "l2": "inputs (512 B/pair) exceed L2 at the full batch; flushed between timed steps as well"}
+
+
 # --------------------------------------------------------------------------------- reference arm (CPU)
 def cpu_reference_pair(y, x, subst, gap, samples, warmup):
     """The reference's own cpu4-mt-diagrow (+ NwTrace1_Plain) from oracle/_ref when it was prebuilt, else the
@@ -162,14 +174,15 @@ def run_reference_arm(args):
         steps = min(steps, 10); warmup = min(warmup, 2)
         g, kind, cores, ms = cpu_reference_pair(y, x, subst, gap, steps, warmup)
         sample = f"{steps} x the full {n}x{m} pair (cpu4-mt-diagrow blocksz 256 fill + NwTrace1_Plain traceback)"
-        cfg = {"workload": f"cfg2: single synthetic protein pair {n}x{m}, score+traceback", "pairs_per_gpu": 1}
+        cfg = pair_config(n, m)
     else:
         npairs = min(args.pairs, 20000)
         pool, offY, lenY, offX, lenX = synth.batch_pairs(0, npairs, 256, 256)
         steps = min(steps, 5); warmup = min(warmup, 1)
         g, kind, cores, ms = cpu_reference_batch(pool, offY, lenY, offX, lenX, subst, gap, steps, warmup)
         sample = f"{steps} x the first {npairs} pairs of the batch (256x256, scores only)"
-        cfg = {"workload": "cfg3: batch of synthetic 256x256 pairs, scores only", "pairs_per_gpu": npairs}
+        cfg = batch_config(args.pairs, args.pairs // max(1, args.gpus))
+        cfg["reference_sample_pairs"] = npairs
     line = {"impl": "reference", "metric": "GCUPS NW linear-gap", "value": g, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": cfg,
@@ -256,9 +269,7 @@ def main():
             return 4
 
         h2d = n + m
-        cfg = {"workload": f"cfg2: single synthetic protein pair {n}x{m} per GPU, score" + ("+traceback" if with_trace else " only"),
-               "pairs_per_gpu": 1, "seeds": "X 2001+10r, Y 2002+10r (splitmix64, independent)", "subst": "blosum62", "gap": gap,
-               "l2": "flushed between timed steps (256 MiB memset)"}
+        cfg = pair_config(n, m, with_trace)
     else:
         per = args.pairs // world
         first = rank * per
@@ -275,9 +286,7 @@ def main():
             return 4 * per
 
         h2d = pool.size + 24 * per
-        cfg = {"workload": f"cfg3: batch of {args.pairs} synthetic 256x256 pairs, scores only, sharded {per}/GPU",
-               "pairs_per_gpu": per, "seeds": "pair p: X 3e6+2p, Y 3e6+2p+1", "subst": "blosum62", "gap": gap,
-               "l2": "inputs (512 B/pair) exceed L2 at the full batch; flushed between timed steps as well"}
+        cfg = batch_config(args.pairs, per)
 
     # ---- device-resident timing ------------------------------------------------------------
     for _ in range(warmup):
@@ -340,7 +349,11 @@ def main():
             "e2e": {"value": e2e, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "int-issue (DPX VIMNMX3, 1 per cell; not hbm/tensor)", "achieved": achieved, "peak": peak, "unit": "GCUPS",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
+                         # (profiles/r1j_ncu_fill_fused_16k.txt: 189 KB for the 16k pair; profiles/r1d_ncu_batch_*.txt: 546 B per pair)
+                         "traffic": (189184 if (args.workload == "pair16k" and args.len == 16384) else
+                                     (546.0 * per if args.workload == "batch256" else None)),
                          "kernel": "nw_fill_kernel" if args.workload == "pair16k" else "nw_batch_kernel", "kernel_ms": fill_ms,
                          "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
