@@ -86,6 +86,7 @@ struct nwb200_ctx {
     bool fuse_map = true;
     bool inline_map = false;
     bool half_map = true;
+    bool grouped = true;
     bool map_is_half = false;
     bool edit_cached = false;
     std::string last_edit;

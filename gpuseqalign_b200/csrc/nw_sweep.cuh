@@ -45,7 +45,7 @@ struct Sched {
     static constexpr int By = 32 * R;                  // rows per band
     static constexpr int LAG = 31 * K;                 // columns lane 31 is behind lane 0
     static constexpr int PD = 2;                       // top-row / letter groups prefetched ahead
-    static constexpr int VR = 128;                     // ints in the top-row ring (4 groups of 32 columns)
+    static constexpr int VR = 256;                     // ints in the top-row ring (8 groups of 32 columns)
     static constexpr int XR = 256;                     // entries in the letter ring (8 groups)
     static constexpr int XM = 32;                      // mirror entries behind the letter ring
     static constexpr int LSTRIDE = 128 * WPL;          // bytes between the profile rows of two letters

@@ -80,6 +80,7 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
     long long ctas_needed = ((a.map ? (a.map_inline ? (long long)g.nb : (a.map_half ? 3LL * g.nb - 2 : 2LL * g.nb - 1)) : (long long)g.nb * a.nq) + g.W - 1) / g.W;
+    if (a.grouped) ctas_needed = (((long long)g.nb + g.W - 1) / g.W) * (1 + (a.map ? (a.map_half ? 2 : 1) : 0));
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
@@ -273,6 +274,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
         }
     }
     c->map_valid = a.map != nullptr; c->map_is_half = a.map != nullptr && half;
+    a.grouped = (c->grouped && !a.map_inline) ? 1 : 0;
     a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
     if (c->dbg_stamps) {
         CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
@@ -361,7 +363,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
 {
     if (!c) return NWB200_ERR_INVALID_VALUE;
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
-    c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0;
+    c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0; c->grouped = (enable & 32) == 0;
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);
