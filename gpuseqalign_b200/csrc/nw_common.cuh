@@ -95,59 +95,8 @@ __device__ __forceinline__ int wait_tagged_count(const unsigned long long* p, un
     return (int)(unsigned)v;
 }
 
-// same, but a miss first sleeps `backoff_ns`: the consumer drops behind its producer once and its
-// later (prefetched) reads hit, instead of re-polling L2 on the critical path of every chunk
-__device__ __forceinline__ int wait_tagged_backoff(const unsigned long long* p, unsigned long long first, unsigned tag, unsigned backoff_ns,
-                                                   unsigned& spins)
-{
-    unsigned long long v = first;
-    if (backoff_ns == 0xffffffffu) return (int)(unsigned)v;     // timing experiment only: no dependency on the band above
-    if ((unsigned)(v >> 32) != tag) {
-        __nanosleep(backoff_ns);
-        v = ld_relaxed64(p);
-        spins += 0x10001u;
-        while ((unsigned)(v >> 32) != tag) {
-            __nanosleep(50);
-            v = ld_relaxed64(p);
-            spins += 1u;
-        }
-    }
-    return (int)(unsigned)v;
-}
-
 // streaming (evict-first) global accesses for header traffic that is written once / read once
 __device__ __forceinline__ void st_cs(int* p, int v) { __stcs(p, v); }
 __device__ __forceinline__ void st_cs4(int4* p, int4 v) { __stcs(p, v); }
-
-// ---- TMA-style bulk copy global -> shared (cp.async.bulk + mbarrier), used for sequence windows
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init()
-{
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}"
-        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 
 }  // namespace nwb
