@@ -67,7 +67,10 @@ __device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned lon
 // Set when a wait for a tagged element gave up (a producer that never publishes must not hang the GPU): the host
 // reports errorInvalidResult.  ~2^21 polls of >= 20 ns + an L2 round trip each are several seconds.
 __device__ int g_wait_timeout = 0;
-constexpr unsigned kMaxPolls = 1u << 21;
+constexpr unsigned kMaxPolls = 1u << 22;
+// Polls do NOT sleep: __nanosleep(20) between two polls made single warps oversleep by 1-3 ms every few launches on B200 (one
+// straggling map unit then held the whole fill launch: 1.2 ms -> 4.5 ms, profiles/r1q_*); a poll is an L2 round trip anyway.
+constexpr unsigned kPollSleepNs = 0;
 
 // returns the value once its tag matches; `first` is an earlier (prefetched) read of *p
 __device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned long long first, unsigned tag)
@@ -75,7 +78,7 @@ __device__ __forceinline__ int wait_tagged(const unsigned long long* p, unsigned
     unsigned long long v = first;
     unsigned polls = 0;
     while ((unsigned)(v >> 32) != tag) {
-        __nanosleep(20);
+        if (kPollSleepNs) __nanosleep(kPollSleepNs);
         v = ld_relaxed64(p);
         if (++polls > kMaxPolls) { g_wait_timeout = 1; break; }
     }
@@ -87,7 +90,7 @@ __device__ __forceinline__ int wait_tagged_count(const unsigned long long* p, un
     unsigned long long v = first;
     unsigned polls = 0;
     while ((unsigned)(v >> 32) != tag) {
-        __nanosleep(20);
+        if (kPollSleepNs) __nanosleep(kPollSleepNs);
         v = ld_relaxed64(p);
         spins++;
         if (++polls > kMaxPolls) { g_wait_timeout = 1; break; }

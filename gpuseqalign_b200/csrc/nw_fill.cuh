@@ -165,36 +165,50 @@ __device__ __forceinline__ void map_unit(const FillArgs& a, unsigned char* warp_
     __syncwarp();
 }
 
-// Shared-memory hand-off of the header row between the warps of one CTA (grouped mode).
+// Shared-memory hand-off of the header row between the warps of one CTA (grouped mode): the top-row ring of the warp below is
+// written quad by quad from inside the step loop of the warp above (nw_sweep.cuh, HAND), so a warp follows the one above it at
+// the distance of the lane pipeline plus one quad.  The only other coupling is a chunk counter for back-pressure.
 struct Handoff {
-    volatile int* ready_in;    // groups the warp above has put into THIS warp's top-row ring (nullptr: top row comes from HR in HBM)
-    volatile int* cons_out;    // this warp's chunk counter, read by the warp above for back-pressure
-    int* next_rin;             // the top-row ring of the warp below (nullptr: nobody below in this CTA)
-    volatile int* ready_out;   // groups this warp has put there
-    volatile int* cons_in;     // the chunk counter of the warp below
+    unsigned rin_s;            // shared-space address of THIS warp's top-row ring (grouped mode; 0: the plain top-row buffer is used)
+    bool self_fed;             // first warp of the CTA: nobody above in this CTA, the warp puts the header row it fetches from HBM into its own ring
+    unsigned cons_out_s;       // shared-space address of the count of chunks this warp has completed, read by the warp above
+    unsigned next_rin_s;       // the ring of the warp below (last warp of the CTA: a sink ring nobody reads)
+    unsigned cons_in_s;        // the chunk counter of the warp below (last warp: a word that holds INT_MAX)
 };
+// All warps of a grouped CTA run the SAME instance of the chunk code (ring in, ring out): three differently specialised copies of
+// the unrolled chunk next to the map units' copy overflowed the instruction cache level that SMs share (no_inst 4 % -> 25 % of the
+// fill's stall samples as soon as map CTAs ran on neighbouring SMs, ncu r1o).
 
-__device__ __forceinline__ void spin_until_ge(volatile int* p, int need)
+__device__ __forceinline__ int spin_until_ge(unsigned addr_s, int need)
 {
     unsigned polls = 0;
-    while (*p < need) {
-        __nanosleep(20);
-        if (++polls > (1u << 26)) { g_wait_timeout = 1; break; }
+    int v;
+#pragma unroll 1
+    while ((v = lds_volatile1(addr_s)) < need) {
+        if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
     }
+    return v;
 }
 
-// Fill of band b of column block q (one warp).
-template <int R, int K>
+// Fill of band b of column block q (one warp).  HAND: bit 0 = the top row arrives through the hand-off ring of the warp above,
+// bit 1 = the bottom row also goes into the ring of the warp below (grouped mode, see Handoff).
+//
+// The chunk loop is written with RUNNING values (ring positions, global pointers, the column the prefetches fetch) and with
+// shared-space byte addresses: written as base + f(lc) through generic pointers, ptxas rebuilt the 64-bit row products and the
+// shared-window bases in every iteration (an S2R and a multiply chain per chunk: 570 clk between two chunks, ncu r1m).
+template <int R, int K, int HAND>
 __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp_smem, const unsigned* sp_tab, const int t, const int lane,
                                           const bool half_map, const Handoff hand)
 {
     using SC = Sched<R, K>;
     constexpr int By = SC::By, VR = SC::VR, XR = SC::XR;
+    constexpr bool HIN = (HAND & 1) != 0, HOUT = (HAND & 2) != 0;
+    static_assert(VR == XR, "the letter ring and the top-row ring advance together");
     WarpSmem<R, K> sm(warp_smem, a.S);
     const int PD = a.pd;
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
     const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
-    const bool smem_in = hand.ready_in != nullptr, smem_out = hand.next_rin != nullptr;
+    constexpr int L4 = SC::L4, HB0 = SC::LAG - SC::L4;     // HB0: ring position of quad 0 of chunk 0
     const int q = t / a.nb, b = t - q * a.nb;             // tickets run block-major: (q, b-1) is always taken before (q, b)
     const int gb = q * a.world + a.rank;                  // global column block
     const long long c0 = (long long)gb * a.wc;            // its first column
@@ -213,7 +227,7 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         const int c = 32 * g + lane;
         sm.put_letter(c, c < m ? (unsigned)__ldg(xb + c) * SC::LSTRIDE : ZOFF);
     }
-    if (!smem_in) for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;      // grouped mode: cleared before the warp above could write into it
+    if constexpr (!HIN) for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;      // HIN: the CTA set the ring to "empty" before the warp above could write into it
 
     Lane<R, 0> st;
     st.oprev = 0; st.oup_next = 0; st.o[0] = 0;
@@ -223,7 +237,6 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         const unsigned* fl = a.recv_flag + (long long)q * a.nb + b;
         const unsigned long long t0 = a.timeout_ns ? globaltimer_ns() : 0ull;
         while (ld_acquire_sys_u32(fl) != a.xtag || (b > 0 && ld_acquire_sys_u32(fl - 1) != a.xtag)) {
-            __nanosleep(200);
             if (a.timeout_ns && globaltimer_ns() - t0 > a.timeout_ns) { if (lane == 0) atomicExch(a.err, 1); break; }
         }
         const int* lp = a.recv + (long long)q * a.recv_stride + 1 + prow0;
@@ -235,18 +248,15 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         for (int r = 0; r < R; r++) st.h[r] = 0;
         st.dprev = 0;
     }
-    const bool consumer = (b > 0);                 // band 0 has row 0 (P = 0) above it
+    const bool from_hbm = !HIN || hand.self_fed;   // this warp fetches the row above from HR in HBM (or it is row 0 of the matrix)
+    const bool consumer = (b > 0) && from_hbm;     // band 0 has row 0 (P = 0) above it
     const unsigned long long* hr_in = a.HR + (long long)q * a.hr_stride + (long long)b * a.ldr + kPadL;
     unsigned long long* hr_out = a.HR + (long long)q * a.hr_stride + (long long)(b + 1) * a.ldr + kPadL;
-    unsigned long long* mid_out = (half_map && b > 0) ? a.MID + (long long)b * a.ldr + kPadL : nullptr;
+    const bool with_mid = half_map && b > 0;
     constexpr int GLM = (15 * K + 31) / 32, SHM = 32 * GLM - 15 * K;
     __syncwarp();
-    // ---- prologue: the first PD groups of the row above
-    const int gcap = (m + 31) / 32;                  // groups that hold real columns
-    if (smem_in) {
-        spin_until_ge(hand.ready_in, PD < gcap ? PD : gcap);
-        __syncwarp();
-    } else if (consumer) {
+    // ---- prologue: the start of the row above
+    if (consumer) {
         {   // head start for the producer: the consumer's prefetches then only touch lines that are complete
             int c = 32 * (PD - 1 + a.slack) + 31;
             if (c > m - 1) c = m - 1;
@@ -254,62 +264,92 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         }
         for (int g = 0; g < PD; g++) {
             const int c = 32 * g + lane;
-            if (c < m) sm.rin[c & (VR - 1)] = wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);
+            if (c < m) sm.rin[(c + (HIN ? SC::LAG : 0)) & (VR - 1)] = wait_tagged(hr_in + c, ld_relaxed64(hr_in + c), a.tag);     // ring: column c sits at c + LAG
         }
     }
     __syncwarp();
+    if constexpr (HIN) {                             // quad 0 of chunk 0: columns -L4 .. 3-L4
+        const int4 v = ring_take(hand.rin_s + 4u * (unsigned)(HB0 & (VR - 1)));
+        st.cq[0] = v.x; st.cq[1] = v.y; st.cq[2] = v.z; st.cq[3] = v.w;
+    } else {
+        st.cq[0] = 0; st.cq[1] = 0; st.cq[2] = 0; st.cq[3] = 0;
+    }
+    __syncwarp();
     if (a.dbg && lane == 0 && q == 0) a.dbg[4 * b + 1] = globaltimer_ns();
-    st.up_next = (lane == 0) ? sm.rin[0] : st.dprev;
+    st.up_next = (lane == 0) ? (HIN ? st.cq[L4] : sm.rin[0]) : st.dprev;
 
+    // ---- running values of the chunk loop
+    const unsigned xs_s = (unsigned)__cvta_generic_to_shared(sm.xs), rin_s = (unsigned)__cvta_generic_to_shared(sm.rin);
+    const unsigned rout_s = (unsigned)__cvta_generic_to_shared(sm.rout), rmid_s = (unsigned)__cvta_generic_to_shared(sm.rmid);
     ChunkIO io;
-    io.prof_lane = sm.prof + lane * 4 * SC::WPL;
-    io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0; io.rmid_chunk = nullptr;
+    io.prof_lane = nullptr; io.xs_lane = nullptr; io.rin_chunk = nullptr; io.rin_next = nullptr; io.rout_chunk = nullptr; io.rmid_chunk = nullptr;
+    io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0;
+    io.prof_s = (unsigned)__cvta_generic_to_shared(sm.prof) + (unsigned)(lane * 4 * SC::WPL);
+    io.hin_s = 0; io.hout_s = 0; io.hout_on = false;
+    unsigned xpos = (unsigned)(-K * lane) & (XR - 1);      // ring position of this lane's letter of step 0
+    unsigned grp = 0;                                      // (32*lc) & (VR-1)
+    unsigned tog = 0;                                      // 128 * (lc & 1): which half of the bottom-row / middle-row staging the chunk fills
+    int cp = 32 * PD + lane;                               // column whose letter / top-row element this iteration prefetches
+    const uint8_t* x_p = xb + cp;
+    const unsigned long long* hr_in_p = hr_in + cp;
+    unsigned long long* hr_out_p = hr_out + lane - 32 * SC::GL;            // where the group that chunk lc completes goes
+    unsigned long long* mid_out_p = a.MID + (long long)b * a.ldr + kPadL + lane - 32 * GLM;
+    // a lane's element of a completed group sits in the half the chunk just filled (lanes >= SH) or in the other one
+    const unsigned po = (lane >= SC::SH) ? 4u * (unsigned)(lane - SC::SH) : 128u + 4u * (unsigned)(32 - SC::SH + lane);
+    const unsigned pm = (lane >= SHM) ? 4u * (unsigned)(lane - SHM) : 128u + 4u * (unsigned)(32 - SHM + lane);
+    constexpr int LCF = (HB0 + 3) / 32;                    // the first quad the warp below reads (columns -L4 ..) is the last quad of chunk LCF
+    int cons_seen = 0;
     int snap_left = a.snap_chunks, snap_k = 0;
     for (int lc = 0; lc < nlc; lc++) {
         // ---- issue the prefetches of chunk lc + PD
-        const int cp = 32 * (lc + PD) + lane;
         unsigned long long pf_hr = 0;
-        const bool want_hr = consumer && !smem_in && cp < m;
-        if (smem_in) {                                  // the warp above writes straight into this warp's ring: wait for groups lc and lc+1
-            spin_until_ge(hand.ready_in, lc + 2 < gcap ? lc + 2 : gcap);
-            if (lane == 0) *hand.cons_out = lc;
-            __syncwarp();
+        const bool want_hr = consumer && cp < m;
+        if constexpr (HOUT) {                           // never overwrite a quad the warp below still has to read
+            if (cons_seen < lc - 8) cons_seen = spin_until_ge(hand.cons_in_s, lc - 8);
+            else cons_seen = lds_volatile1(hand.cons_in_s);
         }
-        if (want_hr) pf_hr = ld_relaxed64(hr_in + cp);
-        const unsigned pf_x = (cp < m) ? (unsigned)__ldg(xb + cp) : (unsigned)a.S;      // scaled when it lands: nothing waits on the load here
+        if (want_hr) pf_hr = ld_relaxed64(hr_in_p);
+        const unsigned pf_x = (cp < m) ? (unsigned)__ldg(x_p) : (unsigned)a.S;      // scaled when it lands: nothing waits on the load here
         // ---- the chunk itself
-        io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
-        io.rin_chunk = sm.rin + ((32 * lc) & (VR - 1));
-        io.rin_next = sm.rin + ((32 * lc + 32) & (VR - 1));
-        io.rout_chunk = sm.rout + (lc & 1) * 32;
-        io.rmid_chunk = mid_out != nullptr ? sm.rmid + (lc & 1) * 32 : nullptr;
-        sweep_chunk<R, K, 0>(st, lane, io, nullptr);
-        __syncwarp();
-        // ---- publish the group of the bottom row that this chunk completed: ONE coalesced 256-byte store
-        if (lc >= SC::GL) {
-            const int v = (lane >= SC::SH) ? sm.rout[(lc & 1) * 32 + lane - SC::SH] : sm.rout[((lc + 1) & 1) * 32 + 32 - SC::SH + lane];
-            st_relaxed64(hr_out + 32 * (lc - SC::GL) + lane, pack_tagged(v, a.tag));
-            if (smem_out) {                             // ... and straight into the ring of the warp below (same CTA): no L2 round trip
-                const int gi = lc - SC::GL;
-                if (gi >= VR / 32 - 1) spin_until_ge(hand.cons_in, gi - (VR / 32 - 1));      // never overwrite a group it still reads
-                hand.next_rin[(32 * gi + lane) & (VR - 1)] = v;
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0) *hand.ready_out = gi + 1;
+        io.xs_s = xs_s + 2u * xpos;
+        io.rin_s = rin_s + 4u * grp;
+        io.rin_next_s = rin_s + 4u * ((grp + 32u) & (VR - 1));
+        io.rout_s = rout_s + tog;
+        io.rmid_s = with_mid ? rmid_s + tog : 0u;
+        // hand-off rings: quads 1..8 of this chunk sit in ONE 32-column group of the ring (HB0 + 4 is a multiple of 32); the warp above
+        // writes every quad up to column 32*nlc + 3 (the tail past its last chunk repeats the frozen last value), so there is no
+        // end-of-row case in the step loop
+        if constexpr (HIN) io.hin_s = hand.rin_s + 4u * ((grp + (unsigned)(HB0 + 4)) & (VR - 1));
+        if constexpr (HOUT) { io.hout_s = hand.next_rin_s + 4u * grp; io.hout_on = lc > LCF; }
+        sweep_chunk<R, K, 0, true, HAND | 4>(st, lane, io, nullptr);
+        if constexpr (HIN) { if (lane == 0) sts_volatile1(hand.cons_out_s, lc + 1); }
+        if constexpr (HOUT) {
+            if (lc == LCF && lane == 31) {
+                const int4 v = lds_volatile4(rout_s + tog + 4u * 28u);
+                sts_volatile4(io.hout_s + 4u * 28u, v.x, v.y, v.z, v.w);
             }
         }
-        // ---- and the group of the middle row (lane 15 is 15*K columns behind lane 0)
-        if (mid_out != nullptr && lc >= GLM) {
-            const int v = (lane >= SHM) ? sm.rmid[(lc & 1) * 32 + lane - SHM] : sm.rmid[((lc + 1) & 1) * 32 + 32 - SHM + lane];
-            st_relaxed64(mid_out + 32 * (lc - GLM) + lane, pack_tagged(v, a.tag));
-        }
+        __syncwarp();
+        // ---- publish the group of the bottom row that this chunk completed: ONE coalesced 256-byte store
+        //      (and the group of the middle row: lane 15 is 15*K columns behind lane 0)
+        int pv = 0, pmv = 0;
+        if (lc >= SC::GL) pv = lds_volatile1(rout_s + (po ^ tog));
+        if (with_mid && lc >= GLM) pmv = lds_volatile1(rmid_s + (pm ^ tog));
         // ---- land the prefetches
-        if (want_hr) {
-            if (a.dbg_mode == 1) sm.rin[cp & (VR - 1)] = (int)(unsigned)pf_hr;
-            else sm.rin[cp & (VR - 1)] = wait_tagged_count(hr_in + cp, pf_hr, a.tag, spins);
+        const unsigned gput = (grp + 32u * (unsigned)PD) & (VR - 1);       // ring position of column cp - lane
+        if (from_hbm) {                                  // (a self-fed ring is re-written group by group: reading a group hands its slot back)
+            int v = 0;
+            if (want_hr) v = (a.dbg_mode == 1) ? (int)(unsigned)pf_hr : wait_tagged_count(hr_in_p, pf_hr, a.tag, spins);
+            if (HIN) sts_volatile1(rin_s + 4u * ((gput + (unsigned)(lane + SC::LAG)) & (VR - 1)), v);
+            else if (consumer) sts_volatile1(rin_s + 4u * (gput + lane), v);
         }
-        else if (consumer && !smem_in) sm.rin[cp & (VR - 1)] = 0;
-        sm.put_letter(cp, pf_x * SC::LSTRIDE);
+        {
+            const unsigned off16 = pf_x * SC::LSTRIDE;
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_s + 2u * (gput + lane)), "h"((unsigned short)off16));
+            if (gput == 0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_s + 2u * (XR + lane)), "h"((unsigned short)off16));   // mirror (XM = 32)
+        }
+        if (lc >= SC::GL) st_relaxed64(hr_out_p, pack_tagged(pv, a.tag));
+        if (with_mid && lc >= GLM) st_relaxed64(mid_out_p, pack_tagged(pmv, a.tag));
         // ---- snapshot of the register state for the traceback
         if (--snap_left == 0) {
             snap_left = a.snap_chunks;
@@ -323,16 +363,20 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
             }
         }
         __syncwarp();
+        xpos = (xpos + 32u) & (XR - 1); grp = (grp + 32u) & (VR - 1); tog ^= 128u;
+        cp += 32; x_p += 32; hr_in_p += 32; hr_out_p += 32; mid_out_p += 32;
     }
     // ---- the first SH elements of the next group were produced by the last chunk (they hold the last real column)
-    if (smem_out && nlc - SC::GL >= VR / 32 - 1) spin_until_ge(hand.cons_in, nlc - SC::GL - (VR / 32 - 1));
-    if (lane < SC::SH) {
-        const int v = sm.rout[((nlc - 1) & 1) * 32 + 32 - SC::SH + lane];
-        st_relaxed64(hr_out + 32 * (nlc - SC::GL) + lane, pack_tagged(v, a.tag));
-        if (smem_out) hand.next_rin[(32 * (nlc - SC::GL) + lane) & (VR - 1)] = v;
+    tog ^= 128u;                                     // the half the last chunk filled
+    if (lane < SC::SH) st_relaxed64(hr_out_p, pack_tagged(lds_volatile1(rout_s + tog + 4u * (unsigned)(32 - SC::SH + lane)), a.tag));
+    if constexpr (HOUT) {
+        // the warp below reads the top row up to column 32*nlc + 3: repeat the frozen last value (P[bottom row][m]) over the three
+        // groups that follow this warp's last quad
+        const int v = __shfl_sync(kFull, st.h[R - 1], 31);
+        if (cons_seen < nlc - 5) cons_seen = spin_until_ge(hand.cons_in_s, nlc - 5);
+        if (lane < 24) sts_volatile4(hand.next_rin_s + 4u * (unsigned)((32 * nlc + 4 * lane) & (VR - 1)), v, v, v, v);
     }
-    if (mid_out != nullptr && lane < SHM)
-        st_relaxed64(mid_out + 32 * (nlc - GLM) + lane, pack_tagged(sm.rmid[((nlc - 1) & 1) * 32 + 32 - SHM + lane], a.tag));
+    if (with_mid && lane < SHM) st_relaxed64(mid_out_p, pack_tagged(lds_volatile1(rmid_s + tog + 4u * (unsigned)(32 - SHM + lane)), a.tag));
     if (a.dbg && lane == 0 && q == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
     // ---- every row is frozen at its last-column value by now
     if (has_right) {
@@ -351,9 +395,9 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
 #pragma unroll
         for (int r = 0; r < R; r++) lp[r] = st.h[r];
     }
-    if (smem_out) { __threadfence_block(); __syncwarp(); if (lane == 0) *hand.ready_out = 0x7fffffff; }
     __syncwarp();
 }
+
 
 template <int R, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
@@ -380,16 +424,15 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         // feeds the warp below through shared memory); map CTA j = map units j*WARPS .. (one warp each, inputs from HBM).
         // Order: F0, then for k >= 1: F(k) followed by the map CTAs of group k-1, finally the map CTAs of the last group.
         __shared__ int s_ticket;
-        __shared__ volatile int s_ready[WARPS];
-        __shared__ volatile int s_cons[WARPS];
+        __shared__ int s_cons[WARPS + 1];       // [WARPS]: INT_MAX, the "consumer" of a warp that feeds nobody
+        const unsigned sink_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)WARPS * SC::warp_smem_bytes(a.S));      // VR ints
         const int nG = (a.nb + WARPS - 1) / WARPS;
         const int mper = with_map ? (half_map ? 2 : 1) : 0;           // map CTAs per fill group
         const int ncta_units = nG * (1 + mper);
         for (;;) {
             __syncthreads();
             if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
-            if (threadIdx.x < WARPS) { s_ready[threadIdx.x] = 0; s_cons[threadIdx.x] = 0; }
-            for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
+            if (threadIdx.x <= WARPS) s_cons[threadIdx.x] = (threadIdx.x < WARPS) ? 0 : 0x7fffffff;
             __syncthreads();
             const int T = s_ticket;
             if (T >= ncta_units) break;
@@ -403,22 +446,26 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
                 if (k < nG) { if (r == 0) fill_k = k; else map_j = mper * (k - 1) + (r - 1); }
                 else map_j = mper * (nG - 1) + (j - per * (nG - 1));
             }
+            // a ring that the warp above feeds starts out empty (-1 in every slot); every other top-row ring is plain data
+            for (int i = lane; i < VR; i += 32) sm.rin[i] = (fill_k >= 0 && w > 0) ? -1 : 0;
+            __syncthreads();
             if (fill_k >= 0) {
                 const int b = fill_k * WARPS + w;
                 if (b < a.nb) {
                     Handoff hand;
-                    hand.ready_in = (w > 0) ? &s_ready[w - 1] : nullptr;
-                    hand.cons_out = &s_cons[w];
+                    hand.rin_s = (unsigned)__cvta_generic_to_shared(sm.rin);
+                    hand.self_fed = (w == 0);
+                    hand.cons_out_s = (unsigned)__cvta_generic_to_shared(&s_cons[w]);
                     const bool below = (w + 1 < WARPS) && (b + 1 < a.nb);
-                    hand.next_rin = below ? WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin : nullptr;
-                    hand.ready_out = &s_ready[w];
-                    hand.cons_in = below ? &s_cons[w + 1] : nullptr;
-                    fill_unit<R, K>(a, warp_smem, sp_tab, b, lane, half_map, hand);
+                    hand.next_rin_s = below ? (unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin) : sink_s;
+                    hand.cons_in_s = (unsigned)__cvta_generic_to_shared(&s_cons[below ? w + 1 : WARPS]);
+                    fill_unit<R, K, 3>(a, warp_smem, sp_tab, b, lane, half_map, hand);
                 }
             } else {
                 const int u = map_j * WARPS + w;                    // map unit: band u / 2, half u % 2 (half maps) or band u
                 const int bb = half_map ? (u >> 1) : u;
                 if (bb >= 1 && bb < a.nb) {
+                    if (a.dbg && lane == 0) a.dbg[4 * (a.nb + u) + 0] = globaltimer_ns();
                     if (half_map) {
                         const int hh = u & 1;
                         map_unit<R / 2, K>(a, warp_smem, sp_tab, (hh ? a.MID : a.HR) + (long long)bb * a.ldr + kPadL, (long long)bb * By + hh * (By / 2),
@@ -427,6 +474,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
                         map_unit<R, K>(a, warp_smem, sp_tab, a.HR + (long long)bb * a.ldr + kPadL, (long long)bb * By,
                                        a.map + (long long)bb * a.ldr + kPadL, bb, lane, false);
                     }
+                    if (a.dbg && lane == 0) a.dbg[4 * (a.nb + u) + 2] = globaltimer_ns();
                 }
             }
         }
@@ -466,7 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             }
             t = (t + 1) >> 1;                                 // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
         }
-        fill_unit<R, K>(a, warp_smem, sp_tab, t, lane, half_map, Handoff{nullptr, nullptr, nullptr, nullptr, nullptr});
+        fill_unit<R, K, 0>(a, warp_smem, sp_tab, t, lane, half_map, Handoff{0u, false, 0u, 0u, 0u});
         __syncwarp();
     }
 }

@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(kScanT) nw_scan_kernel(const ScanArgs a)
                 if (has_left) {
                     if (lane == ((i - 1) & 3)) {
                         unsigned long long v = pend;
-                        while ((unsigned)(v >> 32) != a.tag) {
-                            __nanosleep(40);
+                        while ((unsigned)(v >> 32) != a.tag) {      // no __nanosleep: it oversleeps by milliseconds now and then (nw_common.cuh)
                             v = ld_relaxed64(cin_g + (i - 1));
                             if (a.timeout_ns && globaltimer_ns() - t0 > a.timeout_ns) { atomicExch(a.err, 1); break; }
                         }

@@ -52,6 +52,8 @@ struct Sched {
     static constexpr int SNAP_INTS = R + 4;            // per-lane snapshot: h[R], dprev, up_next, 2 pad
     static constexpr int GL = (LAG + 31) / 32;         // chunks until a 32-column group of the bottom row is complete
     static constexpr int SH = 32 * GL - LAG;           // element of a group that the first step of a chunk produces
+    static constexpr int L4 = LAG & 3;                 // hand-off ring (grouped fill): column c sits at position (c + LAG) & (VR-1), so that the
+                                                       // four values lane 31 produces in steps 4k..4k+3 form one aligned quad
     static_assert(kPadL >= LAG + 1, "header row padding");
     __host__ __device__ static constexpr int nlc(int m) { return (m + LAG + 31) / 32; }      // 32-step chunks per band
     __host__ __device__ static constexpr size_t prof_bytes(int S) { return (size_t)(S + 1) * LSTRIDE; }
@@ -70,6 +72,7 @@ struct Lane {
     int o[MODE == 1 ? R : 1];   // MODE 1: origin labels travelling with h / dprev / up_next
     int oprev;
     int oup_next;
+    int cq[4];       // grouped fill: the last quad of the top row read from the hand-off ring (its tail belongs to the next chunk)
 };
 
 // Warp-private shared memory.
@@ -166,10 +169,62 @@ struct ChunkIO {
     int negg;                        // -gap
     int* dump_lane;                  // MODE 3: &dump[(lane*R)*dump_ld + kPadL + 32*lc - K*lane]: cell (row r, step s) at [r*dump_ld + s]
     long long dump_ld;
+    // ---- grouped fill (HAND != 0): the header row crosses the warps of a CTA through a ring of quads in shared memory.
+    // A quad is written by ONE 16-byte store and is its own ready flag: P >= 0 everywhere, the last word of an empty slot is -1.
+    unsigned hin_s;                  // HAND & 1: shared-space byte address of quad 1 of this chunk in this warp's ring (quad j at + 16*(j-1))
+    unsigned hout_s;                 // HAND & 2: shared-space byte address of the ring of the warp below at position (32*lc) & (VR-1)
+    bool hout_on;                    // HAND & 2: this chunk's quads are read by the warp below (false in the first chunk(s): columns < 0)
+    // ---- HAND & 4: the fill's chunk loop hands over shared-space byte addresses (it keeps them as running values: a chunk loop
+    // written with pointers into the shared window makes ptxas rebuild window bases and 64-bit products in every iteration)
+    unsigned xs_s, prof_s;           // = xs_lane, prof_lane
+    unsigned rin_s, rin_next_s;      // = rin_chunk, rin_next
+    unsigned rout_s, rmid_s;         // = rout_chunk, rmid_chunk (0 = keep nothing)
 };
 
+__device__ __forceinline__ int4 lds_volatile4(unsigned addr)
+{
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_volatile4(unsigned addr, int a, int b, int c, int d)
+{
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void sts_volatile1(unsigned addr, int a)
+{
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(addr), "r"(a));
+}
+__device__ __forceinline__ int lds_volatile1(unsigned addr)
+{
+    int v;
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+// Slow path of a ring read: the quad at `addr` was still empty.  Polls (warp-uniform, bounded like every wait of the engine).
+__device__ __forceinline__ int4 ring_wait(unsigned addr)
+{
+    int4 v;
+    unsigned polls = 0;
+#pragma unroll 1
+    do {
+        v = lds_volatile4(addr);
+        if (++polls > (1u << 22)) { g_wait_timeout = 1; v = make_int4(0, 0, 0, 0); }
+    } while (__any_sync(kFull, v.w < 0));
+    return v;
+}
+// complete read of one quad: wait for the producer, then hand the slot back as empty
+__device__ __forceinline__ int4 ring_take(unsigned addr)
+{
+    int4 v = lds_volatile4(addr);
+    if (__any_sync(kFull, v.w < 0)) v = ring_wait(addr);
+    sts_volatile1(addr + 12, -1);
+    return v;
+}
+constexpr int kRingQG = 2;      // quads per readiness check of a hand-off ring (the producer's stores arrive in order: the last quad vouches for the others)
+
 // One 32-step chunk of one warp.
-template <int R, int K, int MODE, bool TOP = true>
+template <int R, int K, int MODE, bool TOP = true, int HAND = 0>
 __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, const ChunkIO& io, const unsigned* __restrict__ yoff)
 {
     using SC = Sched<R, K>;
@@ -186,7 +241,16 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
     int rv[32 + 8];
     int outv[32];      // lane 31's bottom-row values of this chunk (registers; stored four at a time)
     int outo[32];      // MODE 1: their origin labels
+    constexpr bool SA = (HAND & 4) != 0;
+    static_assert(HAND == 0 || SA, "the hand-off rings are used by the fill, which passes shared-space addresses");
     auto load_pw = [&](int s) {
+        if constexpr (SA) {
+            const unsigned ad = io.prof_s + xo[s];
+            if constexpr (WPL == 1) asm("ld.shared.u32 %0, [%1];" : "=r"(pw[s][0]) : "r"(ad));
+            else if constexpr (WPL == 2) asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(pw[s][0]), "=r"(pw[s][1]) : "r"(ad));
+            else asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(pw[s][0]), "=r"(pw[s][1]), "=r"(pw[s][2]), "=r"(pw[s][3]) : "r"(ad));
+            return;
+        }
         const unsigned char* pp = io.prof_lane + xo[s];
         if constexpr (WPL == 1) pw[s][0] = *reinterpret_cast<const unsigned*>(pp);
         else if constexpr (WPL == 2) { uint2 v = *reinterpret_cast<const uint2*>(pp); pw[s][0] = v.x; pw[s][1] = v.y; }
@@ -195,34 +259,77 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
     auto load_xo = [&](int s) {      // fills xo[s] (and xo[s+1] when the ring position allows a paired load)
         if constexpr (K == 2) {
             if ((s & 1) == 0 && s < 32) {
-                const unsigned v = *reinterpret_cast<const unsigned*>(io.xs_lane + s);
+                unsigned v;
+                if constexpr (SA) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(io.xs_s + 2u * s));
+                else v = *reinterpret_cast<const unsigned*>(io.xs_lane + s);
                 xo[s] = v & 0xffffu; xo[s + 1] = v >> 16;
             }
         } else {
-            if (s < 32) xo[s] = io.xs_lane[s];
+            if (s < 32) {
+                if constexpr (SA) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(xo[s]) : "r"(io.xs_s + 2u * s));
+                else xo[s] = io.xs_lane[s];
+            }
         }
     };
     // rvq[s]: top-row element s of this chunk's group (element 32 = first element of the next group)
     auto load_rv4 = [&](int q) {     // elements 4q .. 4q+3
         if constexpr (TOP) {
             if (q < 8) {
-                const int4 v = *reinterpret_cast<const int4*>(io.rin_chunk + 4 * q);
+                int4 v;
+                if constexpr (SA) v = lds_volatile4(io.rin_s + 16u * q);
+                else v = *reinterpret_cast<const int4*>(io.rin_chunk + 4 * q);
                 rv[4 * q] = v.x; rv[4 * q + 1] = v.y; rv[4 * q + 2] = v.z; rv[4 * q + 3] = v.w;
             } else {
-                rv[32] = io.rin_next[0];
+                if constexpr (SA) rv[32] = lds_volatile1(io.rin_next_s);
+                else rv[32] = io.rin_next[0];
             }
         }
     };
     constexpr int A = (K == 2) ? 1 : 0;          // the shuffle issued at step s carries top-row element s + A
+    constexpr bool HIN = (HAND & 1) != 0, HOUT = (HAND & 2) != 0;
+    static_assert(!HIN || TOP, "a hand-off ring feeds the top row");
+    // HIN: quad j of the chunk = top-row elements 4j-L4 .. 4j-L4+3, first needed at step 4j-3 (both skews).  Quads are taken in
+    // groups of QG: the loads are issued one step before the first quad is needed and land (wait for the producer if the LAST quad
+    // of the group is still empty, then hand that slot back) right before use: the warp follows the warp above at a distance of
+    // one group.  Quad 0 is the previous chunk's quad 8, carried in registers.  (A check per quad costs more than it saves: every
+    // wait loop inside the unrolled chunk makes ptxas rematerialise addresses and constants behind it.)
+    constexpr int L4 = SC::L4, QG = kRingQG;
+    int4 qq[QG];
+    if constexpr (HIN) {
+#pragma unroll
+        for (int e = 0; e < 4 - L4; e++) rv[e] = st.cq[e + L4];
+    }
 #pragma unroll
     for (int s = 0; s < 4; s++) load_xo(s);
-    load_rv4(0); load_rv4(1);
+    if constexpr (!HIN) { load_rv4(0); load_rv4(1); }
 #pragma unroll
     for (int s = 0; s < 2; s++) load_pw(s);
 #pragma unroll
     for (int s = 0; s < 32; s++) {
         if constexpr (K == 2) { if ((s & 1) == 0) load_xo(s + 4); } else { load_xo(s + 3); }
-        if ((s & 3) == 0) load_rv4(s / 4 + 2);
+        if constexpr (HIN) {
+            if ((s & (4 * QG - 1)) == 0) {
+#pragma unroll
+                for (int q = 0; q < QG; q++) qq[q] = lds_volatile4(io.hin_s + 16u * (s / 4 + q));
+            } else if ((s & (4 * QG - 1)) == 1) {
+                const int j0 = (s + 3) / 4;                        // first quad of the group
+                const unsigned alast = io.hin_s + 16u * (j0 - 1 + QG - 1);
+                if (__any_sync(kFull, qq[QG - 1].w < 0)) {
+                    qq[QG - 1] = ring_wait(alast);
+#pragma unroll
+                    for (int q = 0; q < QG - 1; q++) qq[q] = lds_volatile4(io.hin_s + 16u * (j0 - 1 + q));
+                }
+                sts_volatile1(alast + 12u, -1);
+#pragma unroll
+                for (int q = 0; q < QG; q++) {
+                    const int e0 = 4 * (j0 + q) - L4;
+                    rv[e0] = qq[q].x; rv[e0 + 1] = qq[q].y; rv[e0 + 2] = qq[q].z; rv[e0 + 3] = qq[q].w;
+                }
+                if (j0 + QG - 1 == 8) { st.cq[0] = qq[QG - 1].x; st.cq[1] = qq[QG - 1].y; st.cq[2] = qq[QG - 1].z; st.cq[3] = qq[QG - 1].w; }
+            }
+        } else {
+            if ((s & 3) == 0) load_rv4(s / 4 + 2);
+        }
         if (s + 2 < 32) load_pw(s + 2);
         const int rvs = TOP ? rv[s + A] : 0;
         // Rotate-shuffle: lanes 0..30 hand their bottom row to the lane below; lane 31 hands lane 0 its next
@@ -272,11 +379,19 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
         }
         if constexpr (MODE == 0 || MODE == 1) {
             outv[s] = st.h[R - 1];
-            if ((s & 3) == 3 && io.rout_chunk != nullptr && last)
-                *reinterpret_cast<int4*>(io.rout_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
-            if constexpr (MODE == 0) {
-                if ((s & 3) == 3 && io.rmid_chunk != nullptr && lane == 15)
-                    *reinterpret_cast<int4*>(io.rmid_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+            if constexpr (SA) {
+                if ((s & 3) == 3 && io.rout_s != 0 && last) sts_volatile4(io.rout_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+                if ((s & 3) == 3 && io.rmid_s != 0 && lane == 15) sts_volatile4(io.rmid_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+            } else {
+                if ((s & 3) == 3 && io.rout_chunk != nullptr && last)
+                    *reinterpret_cast<int4*>(io.rout_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+                if constexpr (MODE == 0) {
+                    if ((s & 3) == 3 && io.rmid_chunk != nullptr && lane == 15)
+                        *reinterpret_cast<int4*>(io.rmid_chunk + s - 3) = make_int4(outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+                }
+            }
+            if constexpr (HOUT) {      // ... and straight into the ring of the warp below: one quad per four steps
+                if ((s & 3) == 3 && last && io.hout_on) sts_volatile4(io.hout_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
             }
         }
         if constexpr (MODE == 1) {

@@ -62,10 +62,16 @@ int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
 template <int R, int K, int W>
 int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
 {
-    size_t smem = Sched<R, K>::warp_smem_bytes(c->S) * W;
-    if (smem > 48 * 1024) {
+    size_t smem = Sched<R, K>::warp_smem_bytes(c->S) * W + (a.grouped ? sizeof(int) * Sched<R, K>::VR : 0);      // + the sink ring
+    // Few units (the latency-bound single pair): every CTA gets an SM of its own -- the block scheduler does co-locate CTAs while
+    // other SMs are idle (measured: fill warps that share their SM sub-partition with a map warp ran 1.5x slower) -- by asking
+    // for more than half of an SM's shared memory.
+    if (grid <= c->sm_count && smem < 120 * 1024) smem = 120 * 1024;
+    static size_t attr_set = 0;      // per kernel instance (function-local static of the template)
+    if (smem > 48 * 1024 && smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(nw_fill_kernel<R, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(fill)", e);
+        attr_set = smem;
     }
     nw_fill_kernel<R, K, W><<<grid, W * 32, smem, c->stream>>>(a);
     c->launches++;
@@ -277,7 +283,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     a.grouped = (c->grouped && !a.map_inline) ? 1 : 0;
     a.dbg = nullptr; a.dbg_mode = c->dbg_mode & 0xff; a.slack = (c->dbg_mode >> 8) ? (c->dbg_mode >> 8) - 1 : 1;
     if (c->dbg_stamps) {
-        CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
+        CU(c, c->d_dbg.ensure(sizeof(unsigned long long) * 4 * 3 * (size_t)g.nb), NWB200_ERR_MEMORY_ALLOCATION, "alloc debug stamps");
         a.dbg = c->d_dbg.as<unsigned long long>();
     }
     int rc = launch_fill(c, a);
@@ -365,7 +371,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
     c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0; c->grouped = (enable & 32) == 0;
     if (out && c->fill_done && c->d_dbg.p) {
-        int nb = c->g.nb < max_bands ? c->g.nb : max_bands;
+        int nb = 3 * c->g.nb < max_bands ? 3 * c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(out, c->d_dbg.p, sizeof(unsigned long long) * 4 * nb, cudaMemcpyDeviceToHost);
         return nb;

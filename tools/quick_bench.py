@@ -34,6 +34,7 @@ def main():
                     e.fetch_trace()
                     bt = min(bt, e.timing()["trace_calc"])
                 best = min(best, e.timing()["align_calc"])
+                if os.environ.get('VERBOSE'): print(f"   it {it}: fill {e.timing()['align_calc']:.4f}", flush=True)
             print(f"{n}x{m} R={R} W={W} K={K} Bx={Bx} score={s} fill_ms={best:.4f} GCUPS={n*m/best/1e6:.1f}" + (f" trace_ms={bt:.4f}" if TRACE else ""), flush=True)
     e.close()
 
