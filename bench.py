@@ -262,7 +262,7 @@ def main():
                 eng.trace_resident()
 
         def step_e2e():
-            s = eng.align(y, x, keep_headers=True)
+            s = eng.align(y, x, keep_headers=True, with_trace=with_trace)
             if with_trace:
                 e, h = eng.trace()
                 return 4 + len(e) + 4

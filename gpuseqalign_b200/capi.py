@@ -75,6 +75,7 @@ class HeaderInfo:
 
 SCORE_ONLY = 0
 KEEP_HEADERS = 1
+WITH_TRACE = 2
 
 # every symbol declared in include/nwb200.h (tests check the library exports all of them)
 EXPORTS = [
@@ -183,14 +184,17 @@ class Engine:
         self._check(self._L.nwb200_set_scoring(self._h, s.ctypes.data_as(C.POINTER(C.c_int32)), n, int(gap)))
 
     # ---- one pair -----------------------------------------------------------------------
-    def align(self, y: np.ndarray, x: np.ndarray, *, keep_headers: bool = True, params: Optional[Params] = None) -> int:
-        """NwAlignFn: byte letters in, align_cost out (H2D + fill + D2H of the score)."""
+    def align(self, y: np.ndarray, x: np.ndarray, *, keep_headers: bool = True, with_trace: bool = False,
+              params: Optional[Params] = None) -> int:
+        """NwAlignFn: byte letters in, align_cost out (H2D + fill + D2H of the score).  with_trace: the traceback kernels and
+        the copy of the move list are enqueued behind the fill in the same call (``trace()`` then only formats)."""
         y = np.ascontiguousarray(y, dtype=np.uint8); x = np.ascontiguousarray(x, dtype=np.uint8)
         score = C.c_int32(0)
         info = _HdrInfo()
         p = params._c() if params else None
+        flags = (KEEP_HEADERS if keep_headers else SCORE_ONLY) | (WITH_TRACE if with_trace else 0)
         self._check(self._L.nwb200_align_pair_u8(self._h, _ptr(y), y.size, _ptr(x), x.size, C.byref(p) if p else None,
-                                                 KEEP_HEADERS if keep_headers else SCORE_ONLY, C.byref(score), C.byref(info)))
+                                                 flags, C.byref(score), C.byref(info)))
         self.info = HeaderInfo(info.tile_rows, info.tile_cols, info.trows, info.tcols, info.hrow_elems, info.hcol_elems)
         return score.value
 

@@ -63,7 +63,7 @@ struct nwb200_ctx {
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
     // scoring
     std::vector<int32_t> subst;
     int S = 0;
@@ -89,6 +89,9 @@ struct nwb200_ctx {
     bool grouped = true;
     bool map_is_half = false;
     bool edit_cached = false;
+    bool moves_on_host = false;      // the move list of the last traceback has been copied into h_trace already
+    size_t walk_attr_set[8] = {};    // dynamic shared memory size granted to the walk kernel instances so far
+    int* d_timeout_flag = nullptr;   // device address of g_wait_timeout
     std::string last_edit;
     unsigned last_hash = 0;
     // batch

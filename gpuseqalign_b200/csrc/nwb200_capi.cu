@@ -120,6 +120,7 @@ int nwb200_create(nwb200_ctx** out, int device)
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NWB200_ERR_CUDA_GENERAL; }
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete c; return NWB200_ERR_CUDA_GENERAL; }
     if (c->h_small.ensure(4096) != cudaSuccess) { delete c; return NWB200_ERR_MEMORY_ALLOCATION; }
+    if (cudaGetSymbolAddress((void**)&c->d_timeout_flag, g_wait_timeout) != cudaSuccess) { delete c; return NWB200_ERR_CUDA_GENERAL; }
     *out = c;
     return NWB200_SUCCESS;
 }
@@ -234,7 +235,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     if (!c || !c->pair_resident) return fail(c, NWB200_ERR_INVALID_VALUE, "no pair resident on the device");
     cudaSetDevice(c->device);
     const Geometry& g = c->g;
-    const bool keep = (flags & NWB200_KEEP_HEADERS) != 0;
+    const bool keep = (flags & (NWB200_KEEP_HEADERS | NWB200_WITH_TRACE)) != 0;
     {
         const size_t before = c->d_HR.cap;
         CU(c, c->d_HR.ensure(sizeof(unsigned long long) * (size_t)(g.nb + 1) * (size_t)g.ldr), NWB200_ERR_MEMORY_ALLOCATION, "alloc header rows");
@@ -303,17 +304,14 @@ int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
     const unsigned long long* src = c->d_HR.as<unsigned long long>() + (long long)g.nb * g.ldr + kPadL + (g.m - 1);
     CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     CU(c, cudaMemcpyAsync(hs, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
+    CU(c, cudaMemcpyAsync(hs + 1, c->d_timeout_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H wait flag");
     CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel execution", e);
-    {
-        int timed_out = 0;
-        cudaMemcpyFromSymbol(&timed_out, g_wait_timeout, sizeof(int));
-        if (timed_out) {
-            int zero = 0;
-            cudaMemcpyToSymbol(g_wait_timeout, &zero, sizeof(int));
-            return fail(c, NWB200_ERR_INVALID_RESULT, "a band waited too long for its header row (producer never published)");
-        }
+    if (*reinterpret_cast<const int*>(hs + 1) != 0) {
+        int zero = 0;
+        cudaMemcpyToSymbol(g_wait_timeout, &zero, sizeof(int));
+        return fail(c, NWB200_ERR_INVALID_RESULT, "a band waited too long for its header row (producer never published)");
     }
     if ((unsigned)(hs[0] >> 32) != c->epoch) return fail(c, NWB200_ERR_INVALID_RESULT, "the fill did not publish the score element");
     // un-shift: H[n][m] = P[n][m] + (n+m)*gap
@@ -333,6 +331,8 @@ static void fill_hdr_info(const nwb200_ctx* c, nwb200_hdr_info* h)
     h->hcol_elems = (int64_t)g.nb * g.tcols * (1 + g.By);
 }
 
+static int enqueue_moves_copy(nwb200_ctx* c);
+
 int nwb200_align_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8_t* x, int64_t m,
                          const nwb200_params* p, int flags, int32_t* align_cost, nwb200_hdr_info* hdr)
 {
@@ -340,6 +340,12 @@ int nwb200_align_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8
     if (rc) return rc;
     rc = nwb200_fill_resident(c, flags);
     if (rc) return rc;
+    if (flags & NWB200_WITH_TRACE) {
+        rc = nwb200_trace_resident(c);
+        if (rc) return rc;
+        rc = enqueue_moves_copy(c);
+        if (rc) return rc;
+    }
     rc = nwb200_fetch_score(c, align_cost);
     if (rc) return rc;
     fill_hdr_info(c, hdr);
@@ -353,6 +359,12 @@ int nwb200_align_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, c
     if (rc) return rc;
     rc = nwb200_fill_resident(c, flags);
     if (rc) return rc;
+    if (flags & NWB200_WITH_TRACE) {
+        rc = nwb200_trace_resident(c);
+        if (rc) return rc;
+        rc = enqueue_moves_copy(c);
+        if (rc) return rc;
+    }
     rc = nwb200_fetch_score(c, align_cost);
     if (rc) return rc;
     fill_hdr_info(c, hdr);

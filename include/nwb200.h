@@ -68,6 +68,9 @@ typedef struct nwb200_params {
 /* Flags for nwb200_align_pair_*. */
 #define NWB200_SCORE_ONLY   0x0   /* keep only what the score needs                        */
 #define NWB200_KEEP_HEADERS 0x1   /* keep tile header rows/columns for trace / copy_headers */
+#define NWB200_WITH_TRACE   0x2   /* (implies KEEP_HEADERS) the align call also enqueues the traceback kernels and the copy of the move
+                                     list behind the fill, before its single synchronisation: the trace call that follows only
+                                     formats the transcript.  Same results; saves a host round trip per pair. */
 
 /* Geometry of the sparse score-matrix representation kept on the device after an align
  * (what the reference publishes in nw.tileHdrMatRows/Cols, tileHrowLen/tileHcolLen,

@@ -46,6 +46,26 @@ VARIANTS = [(4, 4, 2, 512), (4, 4, 1, 512), (8, 4, 2, 256), (8, 4, 1, 96), (16, 
             (4, 1, 2, 64), (8, 1, 2, 1024), (4, 4, 2, 1024), (8, 4, 2, 64)]
 
 
+def test_align_with_trace_flag(engine, golden, scoring, oracle):
+    """NWB200_WITH_TRACE: the align call enqueues traceback + move copy itself; trace() only formats.  Same results, also when
+    the two forms are mixed on one context and for multi-band pairs."""
+    from gpuseqalign_b200 import synth
+    for c in golden["cases"][::7]:
+        y, x = case_letters(golden, c)
+        assert engine.align(y, x, with_trace=True) == c["score"], (c["y"], c["x"])
+        edit, th = engine.trace()
+        assert edit == c["edit"] and f"{th:08x}" == c["trace_hash"], (c["y"], c["x"])
+    subst = scoring["subst"]["blosum62"]
+    x = synth.letters(71, 3000)
+    y = synth.mutated_copy(x, 72, 2900)
+    exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+    for with_trace in (True, False, True):
+        assert engine.align(y, x, with_trace=with_trace) == exp.score
+        edit, th = engine.trace()
+        assert edit == exp.edit and th == exp.trace_hash
+        assert engine.trace() == (edit, th)         # a second call returns the cached transcript
+
+
 @pytest.mark.parametrize("R,W,K,Bx", VARIANTS)
 def test_random_shapes_all_kernel_variants(engine, scoring, oracle, R, W, K, Bx):
     from gpuseqalign_b200 import Params
