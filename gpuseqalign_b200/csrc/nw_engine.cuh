@@ -90,7 +90,6 @@ struct nwb200_ctx {
     bool map_is_half = false;
     bool edit_cached = false;
     bool moves_on_host = false;      // the move list of the last traceback has been copied into h_trace already
-    size_t walk_attr_set[8] = {};    // dynamic shared memory size granted to the walk kernel instances so far
     int* d_timeout_flag = nullptr;   // device address of g_wait_timeout
     std::string last_edit;
     unsigned last_hash = 0;

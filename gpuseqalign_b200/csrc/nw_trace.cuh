@@ -112,29 +112,77 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------- pass B
-// One thread.  Also lays out the per-band regions of the move buffer: band b can emit at most
+// One warp.  Also lays out the per-band regions of the move buffer: band b can emit at most
 // By + (entry[b] - entry[b-1]) moves (+ slack), band 0 at most By + entry[0].
-__global__ void nw_hop_kernel(const TraceArgs a, int By)
+// The chase itself is a chain of dependent loads (one or two per band), each an L2 round trip of ~0.4 us: 100 us for the 256
+// half-band maps of a 16k pair.  The path runs roughly along the line to the origin, so the warp copies, kHopAhead lookups ahead,
+// the 1024 map entries around the column that line predicts into shared memory (cp.async, one group per lookup): the dependent
+// load then is a shared-memory read.  A wrong guess costs the L2 round trip, never the result.
+constexpr int kHopAhead = 10, kHopWin = 1024;
+__global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int j = a.m;
-    long long off = 0;
-    for (int b = a.nb - 1; b >= 0; b--) {
-        a.entry[b] = j;
-        int jn = 0;
-        if (b > 0 && j > 0) {
-            if (a.map_half) {                         // through the lower half to the band's middle row, then through the upper half
-                const int jm = a.map[(long long)(2 * b + 1) * a.ldr + kPadL + (j - 1)];
-                jn = jm > 0 ? a.map[(long long)(2 * b) * a.ldr + kPadL + (jm - 1)] : 0;
-            } else {
-                jn = a.map[(long long)b * a.ldr + kPadL + (j - 1)];
+    __shared__ __align__(16) int win[kHopAhead][kHopWin];
+    __shared__ int wbase[kHopAhead];
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int nunits = a.map_half ? 2 * a.nb : a.nb;         // unit u = map row u; the units of band 0 are never looked up
+    const int first = a.map_half ? 2 : 1;
+    const int wmax = ((a.m + 31) / 32) * 32 - kHopWin;       // last window start that stays inside a map row
+    const bool pre = wmax >= 0;
+    // copies the window of unit u that the line from (unit u_now, column j_now) to the origin predicts; ALWAYS commits one group
+    auto issue = [&](int u, int j_now, int u_now) {
+        if (pre && u >= first) {
+            int c0 = (int)((float)j_now * __fdividef((float)(u + 1), (float)(u_now + 1))) - kHopWin / 2;      // a guess: float is plenty
+            c0 = c0 < 0 ? 0 : (c0 > wmax ? wmax : c0);
+            c0 &= ~3;
+            const int slot = u % kHopAhead;
+            if (lane == 0) wbase[slot] = c0;
+            const int* src = a.map + (long long)u * a.ldr + kPadL + c0;
+#pragma unroll
+            for (int i = 0; i < kHopWin / 128; i++) {
+                const int e = (i * 32 + lane) * 4;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&win[slot][e])), "l"(src + e));
             }
         }
-        a.off[b] = off;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // map[u][col] once the window of unit u has landed
+    auto lookup = [&](int u, int col) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kHopAhead - 1) : "memory");
+        __syncwarp();
+        int v;
+        const int slot = u % kHopAhead;
+        const int rel = col - wbase[slot];
+        if (pre && rel >= 0 && rel < kHopWin) v = win[slot][rel];
+        else v = __ldcg(a.map + (long long)u * a.ldr + kPadL + col);
+        __syncwarp();
+        return v;
+    };
+    int j = a.m;
+    long long off = 0;
+    int u = nunits - 1;                                       // next unit to look up
+    for (int k = 0; k < kHopAhead; k++) issue(u - k, j, u);
+    for (int b = a.nb - 1; b >= 0; b--) {
+        if (lane == 0) a.entry[b] = j;
+        int jn = 0;
+        if (b > 0) {
+            if (a.map_half) {                         // through the lower half to the band's middle row, then through the upper half
+                int jm = 0;
+                if (j > 0) jm = lookup(2 * b + 1, j - 1);
+                issue(2 * b + 1 - kHopAhead, jm, 2 * b);
+                if (jm > 0) jn = lookup(2 * b, jm - 1);
+                issue(2 * b - kHopAhead, jn, 2 * b - 1);
+            } else {
+                if (j > 0) jn = lookup(b, j - 1);
+                issue(b - kHopAhead, jn, b - 1);
+            }
+        }
+        if (lane == 0) a.off[b] = off;
         off += (long long)By + (j - jn) + 4;
         j = jn;
     }
-    a.off[a.nb] = off;
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (lane == 0) a.off[a.nb] = off;
 }
 
 // ---------------------------------------------------------------------------------------------- pass C

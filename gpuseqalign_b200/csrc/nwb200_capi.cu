@@ -34,7 +34,7 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime
 int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
 {
     Geometry& g = c->g;
-    int R = 0, W = 4, K = 2, Bx = 512;
+    int R = 0, W = 4, K = 2, Bx = (m <= 65536) ? 256 : 512;      // snapshot spacing: the walkers' windows shrink with it, the snapshot volume grows
     if (p) {
         if (p->rows_per_lane) R = p->rows_per_lane;
         if (p->warps_per_block) W = p->warps_per_block;
