@@ -172,19 +172,20 @@ struct Handoff {
     unsigned rin_s;            // shared-space address of THIS warp's top-row ring (grouped mode; 0: the plain top-row buffer is used)
     bool self_fed;             // first warp of the CTA: nobody above in this CTA, the warp puts the header row it fetches from HBM into its own ring
     unsigned cons_out_s;       // shared-space address of the count of chunks this warp has completed, read by the warp above
-    unsigned next_rin_s;       // the ring of the warp below (last warp of the CTA: a sink ring nobody reads)
-    unsigned cons_in_s;        // the chunk counter of the warp below (last warp: a word that holds INT_MAX)
+    unsigned next_rin_s;       // CLUSTER-WINDOW address (mapa) of the ring of the warp below: the next warp of this CTA, warp 0 of the next
+                               // CTA of the thread-block cluster, or a sink ring nobody reads (last band of a cluster unit)
+    unsigned cons_in_s;        // cluster-window address of the chunk counter of the warp below (sink: a word that holds INT_MAX)
 };
 // All warps of a grouped CTA run the SAME instance of the chunk code (ring in, ring out): three differently specialised copies of
 // the unrolled chunk next to the map units' copy overflowed the instruction cache level that SMs share (no_inst 4 % -> 25 % of the
 // fill's stall samples as soon as map CTAs ran on neighbouring SMs, ncu r1o).
 
-__device__ __forceinline__ int spin_until_ge(unsigned addr_s, int need)
+__device__ __forceinline__ int spin_until_ge(unsigned addr_c, int need)
 {
     unsigned polls = 0;
     int v;
 #pragma unroll 1
-    while ((v = lds_volatile1(addr_s)) < need) {
+    while ((v = ldc_volatile1(addr_c)) < need) {
         if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
     }
     return v;
@@ -306,7 +307,7 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         const bool want_hr = consumer && cp < m;
         if constexpr (HOUT) {                           // never overwrite a quad the warp below still has to read
             if (cons_seen < lc - 8) cons_seen = spin_until_ge(hand.cons_in_s, lc - 8);
-            else cons_seen = lds_volatile1(hand.cons_in_s);
+            else cons_seen = ldc_volatile1(hand.cons_in_s);
         }
         if (want_hr) pf_hr = ld_relaxed64(hr_in_p);
         const unsigned pf_x = (cp < m) ? (unsigned)__ldg(x_p) : (unsigned)a.S;      // scaled when it lands: nothing waits on the load here
@@ -326,7 +327,7 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         if constexpr (HOUT) {
             if (lc == LCF && lane == 31) {
                 const int4 v = lds_volatile4(rout_s + tog + 4u * 28u);
-                sts_volatile4(io.hout_s + 4u * 28u, v.x, v.y, v.z, v.w);
+                stc_volatile4(io.hout_s + 4u * 28u, v.x, v.y, v.z, v.w);
             }
         }
         __syncwarp();
@@ -374,7 +375,7 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         // groups that follow this warp's last quad
         const int v = __shfl_sync(kFull, st.h[R - 1], 31);
         if (cons_seen < nlc - 5) cons_seen = spin_until_ge(hand.cons_in_s, nlc - 5);
-        if (lane < 24) sts_volatile4(hand.next_rin_s + 4u * (unsigned)((32 * nlc + 4 * lane) & (VR - 1)), v, v, v, v);
+        if (lane < 24) stc_volatile4(hand.next_rin_s + 4u * (unsigned)((32 * nlc + 4 * lane) & (VR - 1)), v, v, v, v);
     }
     if (with_mid && lane < SHM) st_relaxed64(mid_out_p, pack_tagged(lds_volatile1(rmid_s + tog + 4u * (unsigned)(32 - SHM + lane)), a.tag));
     if (a.dbg && lane == 0 && q == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
@@ -420,22 +421,29 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
     unsigned char* warp_smem = smem_raw + (size_t)w * SC::warp_smem_bytes(a.S);
 
     if (a.grouped) {
-        // ---- grouped mode: CTA-level tickets.  Fill group k = bands k*WARPS .. k*WARPS+WARPS-1 (warp w takes band k*WARPS+w and
-        // feeds the warp below through shared memory); map CTA j = map units j*WARPS .. (one warp each, inputs from HBM).
-        // Order: F0, then for k >= 1: F(k) followed by the map CTAs of group k-1, finally the map CTAs of the last group.
+        // ---- grouped mode: CLUSTER-level tickets (a cluster of CL CTAs; CL = 1 without a cluster launch).  Fill unit k = bands
+        // k*CL*WARPS .. (k+1)*CL*WARPS-1: CTA r of the cluster takes the four bands (k*CL + r)*WARPS + w, warp w feeds the warp below
+        // through its ring in shared memory, the last warp of CTA r feeds warp 0 of CTA r+1 through distributed shared memory
+        // (the same ring, st.shared::cluster).  Map unit j = CL*WARPS map units (one warp each, inputs from HBM).
+        // Order: F0, then for k >= 1: F(k) followed by the map units of fill unit k-1, finally the map units of the last fill unit.
         __shared__ int s_ticket;
         __shared__ int s_cons[WARPS + 1];       // [WARPS]: INT_MAX, the "consumer" of a warp that feeds nobody
         const unsigned sink_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)WARPS * SC::warp_smem_bytes(a.S));      // VR ints
-        const int nG = (a.nb + WARPS - 1) / WARPS;
-        const int mper = with_map ? (half_map ? 2 : 1) : 0;           // map CTAs per fill group
-        const int ncta_units = nG * (1 + mper);
+        const unsigned CL = cluster_size(), crank = cluster_rank();
+        const int per_unit = (int)CL * WARPS;
+        const int nG = (a.nb + per_unit - 1) / per_unit;
+        const int mper = with_map ? (half_map ? 2 : 1) : 0;           // map units per fill unit
+        const int ncl_units = nG * (1 + mper);
         for (;;) {
-            __syncthreads();
-            if (threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
+            if (CL > 1) cluster_sync_all(); else __syncthreads();      // everybody is done with the previous unit (and with my shared memory)
+            if (crank == 0 && threadIdx.x == 0) s_ticket = atomicAdd(a.ticket, 1);
             if (threadIdx.x <= WARPS) s_cons[threadIdx.x] = (threadIdx.x < WARPS) ? 0 : 0x7fffffff;
-            __syncthreads();
-            const int T = s_ticket;
-            if (T >= ncta_units) break;
+            if (CL > 1) cluster_sync_all(); else __syncthreads();
+            const int T = (crank == 0) ? s_ticket : ldc_volatile1(map_to_cta((unsigned)__cvta_generic_to_shared(&s_ticket), 0));
+            if (T >= ncl_units) {
+                if (CL > 1) cluster_sync_all();      // CTA 0 must not exit while the others still read its ticket
+                break;
+            }
             // decode
             int fill_k = -1, map_j = -1;
             if (T == 0) fill_k = 0;
@@ -446,23 +454,32 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
                 if (k < nG) { if (r == 0) fill_k = k; else map_j = mper * (k - 1) + (r - 1); }
                 else map_j = mper * (nG - 1) + (j - per * (nG - 1));
             }
-            // a ring that the warp above feeds starts out empty (-1 in every slot); every other top-row ring is plain data
-            for (int i = lane; i < VR; i += 32) sm.rin[i] = (fill_k >= 0 && w > 0) ? -1 : 0;
-            __syncthreads();
+            // a ring that another warp feeds starts out empty (-1 in every slot); every other top-row ring is plain data
+            for (int i = lane; i < VR; i += 32) sm.rin[i] = (fill_k >= 0 && (w > 0 || crank > 0)) ? -1 : 0;
+            if (CL > 1) cluster_sync_all(); else __syncthreads();
             if (fill_k >= 0) {
-                const int b = fill_k * WARPS + w;
+                const int b = (fill_k * (int)CL + (int)crank) * WARPS + w;
                 if (b < a.nb) {
                     Handoff hand;
                     hand.rin_s = (unsigned)__cvta_generic_to_shared(sm.rin);
-                    hand.self_fed = (w == 0);
+                    hand.self_fed = (w == 0 && crank == 0);
                     hand.cons_out_s = (unsigned)__cvta_generic_to_shared(&s_cons[w]);
-                    const bool below = (w + 1 < WARPS) && (b + 1 < a.nb);
-                    hand.next_rin_s = below ? (unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin) : sink_s;
-                    hand.cons_in_s = (unsigned)__cvta_generic_to_shared(&s_cons[below ? w + 1 : WARPS]);
+                    const bool last_of_unit = (w + 1 == WARPS) && (crank + 1 == CL);
+                    const bool below = !last_of_unit && (b + 1 < a.nb);
+                    if (!below) {
+                        hand.next_rin_s = map_to_cta(sink_s, crank);
+                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[WARPS]), crank);
+                    } else if (w + 1 < WARPS) {
+                        hand.next_rin_s = map_to_cta((unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin), crank);
+                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[w + 1]), crank);
+                    } else {                            // warp 0 of the next CTA of the cluster (same layout: my own warp 0's addresses, mapped)
+                        hand.next_rin_s = map_to_cta((unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(smem_raw, a.S).rin), crank + 1);
+                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[0]), crank + 1);
+                    }
                     fill_unit<R, K, 3>(a, warp_smem, sp_tab, b, lane, half_map, hand);
                 }
             } else {
-                const int u = map_j * WARPS + w;                    // map unit: band u / 2, half u % 2 (half maps) or band u
+                const int u = (map_j * (int)CL + (int)crank) * WARPS + w;   // map unit: band u / 2, half u % 2 (half maps) or band u
                 const int bb = half_map ? (u >> 1) : u;
                 if (bb >= 1 && bb < a.nb) {
                     if (a.dbg && lane == 0) a.dbg[4 * (a.nb + u) + 0] = globaltimer_ns();

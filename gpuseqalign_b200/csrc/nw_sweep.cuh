@@ -172,7 +172,7 @@ struct ChunkIO {
     // ---- grouped fill (HAND != 0): the header row crosses the warps of a CTA through a ring of quads in shared memory.
     // A quad is written by ONE 16-byte store and is its own ready flag: P >= 0 everywhere, the last word of an empty slot is -1.
     unsigned hin_s;                  // HAND & 1: shared-space byte address of quad 1 of this chunk in this warp's ring (quad j at + 16*(j-1))
-    unsigned hout_s;                 // HAND & 2: shared-space byte address of the ring of the warp below at position (32*lc) & (VR-1)
+    unsigned hout_s;                 // HAND & 2: cluster-window byte address of the ring of the warp below at position (32*lc) & (VR-1)
     bool hout_on;                    // HAND & 2: this chunk's quads are read by the warp below (false in the first chunk(s): columns < 0)
     // ---- HAND & 4: the fill's chunk loop hands over shared-space byte addresses (it keeps them as running values: a chunk loop
     // written with pointers into the shared window makes ptxas rebuild window bases and 64-bit products in every iteration)
@@ -190,6 +190,40 @@ __device__ __forceinline__ int4 lds_volatile4(unsigned addr)
 __device__ __forceinline__ void sts_volatile4(unsigned addr, int a, int b, int c, int d)
 {
     asm volatile("st.volatile.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+// the same through the cluster window: `addr` comes from mapa (the ring / counter of a warp in ANOTHER CTA of the thread-block
+// cluster, or in this one -- a CTA's own shared memory is part of the window)
+__device__ __forceinline__ void stc_volatile4(unsigned addr, int a, int b, int c, int d)
+{
+    asm volatile("st.volatile.shared::cluster.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ int ldc_volatile1(unsigned addr)
+{
+    int v;
+    asm volatile("ld.volatile.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned map_to_cta(unsigned addr, unsigned cta_rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_rank()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_size()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void sts_volatile1(unsigned addr, int a)
 {
@@ -391,7 +425,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
                 }
             }
             if constexpr (HOUT) {      // ... and straight into the ring of the warp below: one quad per four steps
-                if ((s & 3) == 3 && last && io.hout_on) sts_volatile4(io.hout_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+                if ((s & 3) == 3 && last && io.hout_on) stc_volatile4(io.hout_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
             }
         }
         if constexpr (MODE == 1) {

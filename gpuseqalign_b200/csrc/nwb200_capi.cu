@@ -60,7 +60,7 @@ int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
 }
 
 template <int R, int K, int W>
-int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
+int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
 {
     size_t smem = Sched<R, K>::warp_smem_bytes(c->S) * W + (a.grouped ? sizeof(int) * Sched<R, K>::VR : 0);      // + the sink ring
     // Few units (the latency-bound single pair): every CTA gets an SM of its own -- the block scheduler does co-locate CTAs while
@@ -73,9 +73,21 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid)
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(fill)", e);
         attr_set = smem;
     }
-    nw_fill_kernel<R, K, W><<<grid, W * 32, smem, c->stream>>>(a);
+    cudaError_t e = cudaSuccess;
+    if (cluster > 1) {
+        // thread-block clusters: the hand-off ring of the last warp of a CTA is the shared memory of the next CTA of its cluster
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(W * 32); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, nw_fill_kernel<R, K, W>, a);
+    } else {
+        nw_fill_kernel<R, K, W><<<grid, W * 32, smem, c->stream>>>(a);
+        e = cudaGetLastError();
+    }
     c->launches++;
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel launch", e);
     return NWB200_SUCCESS;
 }
@@ -86,11 +98,20 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     // persistent grid: one CTA of W warps per SM while that covers every band (each warp alone on its SM
     // sub-partition: the single pair is latency bound), otherwise up to 16 warps per SM
     long long ctas_needed = ((a.map ? (a.map_inline ? (long long)g.nb : (a.map_half ? 3LL * g.nb - 2 : 2LL * g.nb - 1)) : (long long)g.nb * a.nq) + g.W - 1) / g.W;
-    if (a.grouped) ctas_needed = (((long long)g.nb + g.W - 1) / g.W) * (1 + (a.map ? (a.map_half ? 2 : 1) : 0));
+    int cluster = 1;
+    if (a.grouped) {
+        // cluster size: as many CTAs as a chain of bands can use, at most the portable 8
+        if (c->cluster_max > 1 && g.W == 4) cluster = g.nb > 16 ? 8 : (g.nb > 8 ? 4 : (g.nb > 4 ? 2 : 1));
+        if (cluster > c->cluster_max) cluster = c->cluster_max;
+        const long long per = (long long)g.W * cluster;
+        ctas_needed = (((long long)g.nb + per - 1) / per) * (1 + (a.map ? (a.map_half ? 2 : 1) : 0)) * cluster;
+    }
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
-#define NWB_CASE(R_, K_, W_) if (g.R == R_ && g.K == K_ && g.W == W_) return launch_fill_t<R_, K_, W_>(c, a, (int)grid)
+    grid -= grid % cluster;
+    if (grid < cluster) grid = cluster;
+#define NWB_CASE(R_, K_, W_) if (g.R == R_ && g.K == K_ && g.W == W_) return launch_fill_t<R_, K_, W_>(c, a, (int)grid, cluster)
     NWB_CASE(4, 2, 4); NWB_CASE(4, 1, 4); NWB_CASE(8, 2, 4); NWB_CASE(8, 1, 4); NWB_CASE(16, 2, 4); NWB_CASE(16, 1, 4);
     NWB_CASE(4, 2, 1); NWB_CASE(8, 2, 1);
 #undef NWB_CASE
@@ -382,6 +403,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
     if (!c) return NWB200_ERR_INVALID_VALUE;
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
     c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0; c->grouped = (enable & 32) == 0;
+    c->cluster_max = (enable & 64) ? 1 : ((enable & 128) ? 2 : ((enable & 256) ? 4 : 8));
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = 3 * c->g.nb < max_bands ? 3 * c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);
