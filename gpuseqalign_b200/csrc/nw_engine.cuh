@@ -79,7 +79,7 @@ struct nwb200_ctx {
     nwb::DevBuf d_y, d_x, d_HR, d_snap, d_lastcol, d_sync;
     nwb::PinBuf h_stage, h_small, h_trace;
     // traceback
-    nwb::DevBuf d_map, d_MID, d_tmeta, d_ops, d_dense, d_export, d_HR2;
+    nwb::DevBuf d_map, d_MID, d_tmeta, d_ops, d_dense, d_export, d_HR2, d_cut;
     nwb::PinBuf h_export;
     bool trace_done = false;
     bool map_valid = false;          // the last fill launch also produced the origin maps

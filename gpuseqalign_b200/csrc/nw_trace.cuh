@@ -43,6 +43,13 @@ struct TraceArgs {
     unsigned char* dense;            // packed backward move list
     long long* total;                // [2]: total moves, consistency flag
     int map_half;                    // 1: map rows 2b (upper half of band b) and 2b+1 (lower half); 0: one map row per band
+    // ---- segmented maps (nw_map_kernel): a band's map is computed in nseg independent column segments, every segment resuming
+    // the sweep from a snapshot of the fill.  A path that leaves a segment through its LEFT cut carries the negative label
+    // -(1 + lane*(R+2) + slot) of the cut cell (slot r < R: the lane's row r, slot R: the cell above its first row one column
+    // to the left, slot R+1: the same cell of the cut column); cut[((b*nseg + j)*32 + lane)*(R+2) + slot] holds the label that
+    // cell got in segment j, its own left neighbour: the chase follows these until it meets a top-row column.
+    int* cut;
+    int nseg;
 };
 
 // Loads a plain (already complete) header-row group into the top-row ring.
@@ -60,6 +67,10 @@ __device__ __forceinline__ void load_letter_group(WarpSmem<R, K>& sm, const uint
 }
 
 // ---------------------------------------------------------------------------------------------- pass A
+// Units = (band, column segment).  Bands are independent once the fill is done, and so are the segments of a band: the fill's
+// snapshots hold the register state at every segment boundary.  One warp per band (782 warps for a 200k pair) left the machine
+// at one warp per SM sub-partition, i.e. at a third of its issue rate (28 ms for the maps against 12.7 ms for the fill); the
+// segments give as many units as the throughput regime needs.
 template <int R, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
 {
@@ -72,28 +83,46 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int m = a.m, nlc = SC::nlc(m);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
-    const int nwarps = gridDim.x * WARPS;
-    // band 0 needs no map: the walker of band 0 ends the path itself
-    for (int b = 1 + blockIdx.x * WARPS + w; b < a.nb; b += nwarps) {
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    const int nseg = a.nseg;
+    const long long nunits = (long long)(a.nb - 1) * nseg;       // band 0 needs no map: the walker of band 0 ends the path itself
+    for (long long u = (long long)blockIdx.x * WARPS + w; u < nunits; u += nwarps) {
+        const int b = 1 + (int)(u / nseg), seg = (int)(u % nseg);
+        const int lc0 = seg * a.snap_chunks;
+        int lc1 = lc0 + a.snap_chunks;
+        if (seg == nseg - 1 || lc1 > nlc) lc1 = nlc;
         const long long prow0 = (long long)b * By + (long long)lane * R;
+        __syncwarp();
         build_profile<R, K>(sm, sp_tab, a.S, a.y, prow0 - a.pad, a.n, lane, nullptr);
         const unsigned long long* hr_in = a.HR + (long long)b * a.ldr + kPadL;
-        for (int g = -2; g < PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
+        for (int g = lc0 - 2 * K; g < lc0 + PD; g++) load_letter_group<R, K>(sm, a.x, g, m, lane, ZOFF);
         for (int i = lane; i < VR; i += 32) sm.rin[i] = 0;
         __syncwarp();
-        for (int g = 0; g < PD; g++) load_top_group<R, K>(sm, hr_in, g, m, lane);
+        for (int g = lc0; g < lc0 + PD; g++) load_top_group<R, K>(sm, hr_in, g, m, lane);
         __syncwarp();
         Lane<R, 1> st;
+        if (lc0 > 0) {                                // resume from the fill's snapshot; the cells of the cut get fresh (negative) labels
+            const int* sp = a.snap + (((long long)b * a.nsnap + (seg - 1)) * 32 + lane) * SC::SNAP_INTS;
+            const int id0 = -(1 + lane * (R + 2));
 #pragma unroll
-        for (int r = 0; r < R; r++) { st.h[r] = 0; st.o[r] = 0; }
-        st.dprev = 0; st.oprev = 0;
-        st.up_next = (lane == 0) ? sm.rin[0] : 0;
-        st.oup_next = (lane == 0) ? 1 : 0;
+            for (int r = 0; r < R; r++) { st.h[r] = sp[r]; st.o[r] = id0 - r; }
+            st.dprev = sp[R];
+            st.up_next = sp[R + 1];
+            // lane 0's upper neighbours are cells of the band's top row: their label is their own column
+            st.oprev = (lane == 0) ? 32 * lc0 : id0 - R;
+            st.oup_next = (lane == 0) ? 32 * lc0 + 1 : id0 - (R + 1);
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; r++) { st.h[r] = 0; st.o[r] = 0; }
+            st.dprev = 0; st.oprev = 0;
+            st.up_next = (lane == 0) ? sm.rin[0] : 0;
+            st.oup_next = (lane == 0) ? 1 : 0;
+        }
         ChunkIO io;
         io.prof_lane = sm.prof + lane * 4 * SC::WPL;
         io.rout_chunk = nullptr; io.rmid_chunk = nullptr; io.dirs_lane = nullptr; io.negg = a.negg;
         int* map_row = a.map + (long long)b * a.ldr + kPadL;
-        for (int lc = 0; lc < nlc; lc++) {
+        for (int lc = lc0; lc < lc1; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             const int pf_top = (cp < m) ? (int)(unsigned)__ldg(hr_in + cp) : 0;
             const unsigned pf_x = (cp < m) ? (unsigned)__ldg(a.x + cp) : (unsigned)a.S;      // scaled when it lands
@@ -108,6 +137,13 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
             sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }
+        if (seg + 1 < nseg) {                         // the labels of this segment's right cut, for the segment to the right
+            int* cp = a.cut + (((long long)b * nseg + seg) * 32 + lane) * (R + 2);
+#pragma unroll
+            for (int r = 0; r < R; r++) cp[r] = st.o[r];
+            cp[R] = st.oprev;
+            cp[R + 1] = st.oup_next;
+        }
     }
 }
 
@@ -119,7 +155,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
 // the 1024 map entries around the column that line predicts into shared memory (cp.async, one group per lookup): the dependent
 // load then is a shared-memory read.  A wrong guess costs the L2 round trip, never the result.
 constexpr int kHopAhead = 10, kHopWin = 1024;
-__global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By)
+__global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, int cut_lag, int cut_slots)      // cut_lag = 31*K, cut_slots = R+2
 {
     __shared__ __align__(16) int win[kHopAhead][kHopWin];
     __shared__ int wbase[kHopAhead];
@@ -173,7 +209,18 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By)
                 if (jm > 0) jn = lookup(2 * b, jm - 1);
                 issue(2 * b - kHopAhead, jn, 2 * b - 1);
             } else {
-                if (j > 0) jn = lookup(b, j - 1);
+                if (j > 0) {
+                    jn = lookup(b, j - 1);
+                    // a negative label: the path left the segment that computed it through its left cut -- follow the cut cell's
+                    // label in the segment(s) to the left until it is a top-row column (a dependent load each)
+                    int sg = ((j - 1) + cut_lag) / (32 * a.snap_chunks);
+                    if (sg > a.nseg - 1) sg = a.nseg - 1;
+                    while (jn < 0 && sg > 0) {
+                        sg--;
+                        jn = __ldcg(a.cut + ((long long)b * a.nseg + sg) * 32 * cut_slots + (-jn - 1));
+                    }
+                    if (jn < 0) jn = 0;               // cannot happen (segment 0 has no cut)
+                }
                 issue(b - kHopAhead, jn, b - 1);
             }
         }

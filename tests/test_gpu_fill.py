@@ -46,6 +46,31 @@ VARIANTS = [(4, 4, 2, 512), (4, 4, 1, 512), (8, 4, 2, 256), (8, 4, 1, 96), (16, 
             (4, 1, 2, 64), (8, 1, 2, 1024), (4, 4, 2, 1024), (8, 4, 2, 64)]
 
 
+@pytest.mark.parametrize("R,K,Bx", [(4, 2, 32), (8, 2, 64), (4, 1, 96), (16, 2, 128)])
+def test_segmented_maps_follow_paths_across_cuts(scoring, oracle, R, K, Bx):
+    """The separate map kernel (pairs with more bands than the fused launch shadows) computes a band's map in independent column
+    segments that resume from the fill's snapshots; a path that leaves a segment through its left cut is followed through the
+    cut labels.  Small snapshot spacings + long horizontal runs (y much shorter than x, and a 3000-column insertion) make
+    paths cross many cuts inside one band."""
+    import ctypes as C
+    from gpuseqalign_b200 import Engine, Params, synth
+    subst = scoring["subst"]["blosum62"]
+    e = Engine(0)
+    e.set_scoring(subst, -11)
+    e._L.nwb200_debug_band_stamps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    e._L.nwb200_debug_band_stamps(e._h, 4, 0, None, 0)          # origin maps in their own launch
+    x0 = synth.letters(91, 2600)
+    cases = [(synth.letters(92, 700), synth.letters(93, 5000)),                                        # 7 columns per row
+             (synth.mutated_copy(x0, 94, 2500), np.concatenate([x0[:1200], synth.letters(95, 3000), x0[1200:]])),
+             (synth.letters(96, 1500), synth.letters(97, 1400))]
+    for y, x in cases:
+        exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+        assert e.align(y, x, params=Params(R, 4, Bx, K)) == exp.score
+        edit, th = e.trace()
+        assert edit == exp.edit and th == exp.trace_hash, (R, K, Bx, y.size, x.size)
+    e.close()
+
+
 def test_align_with_trace_flag(engine, golden, scoring, oracle):
     """NWB200_WITH_TRACE: the align call enqueues traceback + move copy itself; trace() only formats.  Same results, also when
     the two forms are mixed on one context and for multi-band pairs."""
