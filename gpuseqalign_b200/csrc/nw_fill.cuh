@@ -172,20 +172,26 @@ struct Handoff {
     unsigned rin_s;            // shared-space address of THIS warp's top-row ring (grouped mode; 0: the plain top-row buffer is used)
     bool self_fed;             // first warp of the CTA: nobody above in this CTA, the warp puts the header row it fetches from HBM into its own ring
     unsigned cons_out_s;       // shared-space address of the count of chunks this warp has completed, read by the warp above
-    unsigned next_rin_s;       // CLUSTER-WINDOW address (mapa) of the ring of the warp below: the next warp of this CTA, warp 0 of the next
+    int* next_rin_g;           // GENERIC pointer (mapa.u64) to the ring of the warp below: the next warp of this CTA, warp 0 of the next
                                // CTA of the thread-block cluster, or a sink ring nobody reads (last band of a cluster unit)
-    unsigned cons_in_s;        // cluster-window address of the chunk counter of the warp below (sink: a word that holds INT_MAX)
+    const int* cons_in_g;      // generic pointer to the chunk counter of the warp below (sink: a word that holds INT_MAX)
 };
 // All warps of a grouped CTA run the SAME instance of the chunk code (ring in, ring out): three differently specialised copies of
 // the unrolled chunk next to the map units' copy overflowed the instruction cache level that SMs share (no_inst 4 % -> 25 % of the
 // fill's stall samples as soon as map CTAs ran on neighbouring SMs, ncu r1o).
 
-__device__ __forceinline__ int spin_until_ge(unsigned addr_c, int need)
+__device__ __forceinline__ int ld_counter(const int* p)     // a counter in (possibly another CTA's) shared memory
+{
+    int v;
+    asm volatile("ld.relaxed.cluster.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int spin_until_ge(const int* p, int need)
 {
     unsigned polls = 0;
     int v;
 #pragma unroll 1
-    while ((v = ldc_volatile1(addr_c)) < need) {
+    while ((v = ld_counter(p)) < need) {
         if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
     }
     return v;
@@ -286,7 +292,14 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
     io.prof_lane = nullptr; io.xs_lane = nullptr; io.rin_chunk = nullptr; io.rin_next = nullptr; io.rout_chunk = nullptr; io.rmid_chunk = nullptr;
     io.map_out = nullptr; io.org0 = 0; io.dirs_lane = nullptr; io.negg = 0; io.dump_lane = nullptr; io.dump_ld = 0;
     io.prof_s = (unsigned)__cvta_generic_to_shared(sm.prof) + (unsigned)(lane * 4 * SC::WPL);
-    io.hin_s = 0; io.hout_s = 0; io.hout_on = false;
+    io.hin_s = 0; io.hout_p = nullptr; io.hout_on = false;
+    io.kconst_s = (unsigned)__cvta_generic_to_shared(sm.kconst);
+    if constexpr (HAND != 0) {
+        if (lane < 4) sm.kconst[lane] = 1 << (8 * lane);
+        if (lane == 4) sm.kconst[4] = -1;
+        sm.kconst[8 + lane] = (lane == 31) ? -1 : 0;
+        __syncwarp();
+    }
     unsigned xpos = (unsigned)(-K * lane) & (XR - 1);      // ring position of this lane's letter of step 0
     unsigned grp = 0;                                      // (32*lc) & (VR-1)
     unsigned tog = 0;                                      // 128 * (lc & 1): which half of the bottom-row / middle-row staging the chunk fills
@@ -301,13 +314,14 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
     constexpr int LCF = (HB0 + 3) / 32;                    // the first quad the warp below reads (columns -L4 ..) is the last quad of chunk LCF
     int cons_seen = 0;
     int snap_left = a.snap_chunks, snap_k = 0;
-    for (int lc = 0; lc < nlc; lc++) {
+    int lc = 0;
+    for (int left = nlc; left > 0; left--, lc++) {        // (a running count: written as lc < nlc, ptxas recomputes nlc from m every iteration)
         // ---- issue the prefetches of chunk lc + PD
         unsigned long long pf_hr = 0;
         const bool want_hr = consumer && cp < m;
         if constexpr (HOUT) {                           // never overwrite a quad the warp below still has to read
-            if (cons_seen < lc - 8) cons_seen = spin_until_ge(hand.cons_in_s, lc - 8);
-            else cons_seen = ldc_volatile1(hand.cons_in_s);
+            if (cons_seen < lc - 8) cons_seen = spin_until_ge(hand.cons_in_g, lc - 8);
+            else cons_seen = ld_counter(hand.cons_in_g);
         }
         if (want_hr) pf_hr = ld_relaxed64(hr_in_p);
         const unsigned pf_x = (cp < m) ? (unsigned)__ldg(x_p) : (unsigned)a.S;      // scaled when it lands: nothing waits on the load here
@@ -321,13 +335,13 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         // writes every quad up to column 32*nlc + 3 (the tail past its last chunk repeats the frozen last value), so there is no
         // end-of-row case in the step loop
         if constexpr (HIN) io.hin_s = hand.rin_s + 4u * ((grp + (unsigned)(HB0 + 4)) & (VR - 1));
-        if constexpr (HOUT) { io.hout_s = hand.next_rin_s + 4u * grp; io.hout_on = lc > LCF; }
+        if constexpr (HOUT) { io.hout_p = hand.next_rin_g + grp; io.hout_on = lc > LCF; }
         sweep_chunk<R, K, 0, true, HAND | 4>(st, lane, io, nullptr);
         if constexpr (HIN) { if (lane == 0) sts_volatile1(hand.cons_out_s, lc + 1); }
         if constexpr (HOUT) {
             if (lc == LCF && lane == 31) {
                 const int4 v = lds_volatile4(rout_s + tog + 4u * 28u);
-                stc_volatile4(io.hout_s + 4u * 28u, v.x, v.y, v.z, v.w);
+                stg_quad(io.hout_p + 28, v.x, v.y, v.z, v.w);
             }
         }
         __syncwarp();
@@ -349,8 +363,8 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_s + 2u * (gput + lane)), "h"((unsigned short)off16));
             if (gput == 0) asm volatile("st.shared.u16 [%0], %1;" ::"r"(xs_s + 2u * (XR + lane)), "h"((unsigned short)off16));   // mirror (XM = 32)
         }
-        if (lc >= SC::GL) st_relaxed64(hr_out_p, pack_tagged(pv, a.tag));
-        if (with_mid && lc >= GLM) st_relaxed64(mid_out_p, pack_tagged(pmv, a.tag));
+        if (lc >= SC::GL) st_tagged(hr_out_p, pv, a.tag);
+        if (with_mid && lc >= GLM) st_tagged(mid_out_p, pmv, a.tag);
         // ---- snapshot of the register state for the traceback
         if (--snap_left == 0) {
             snap_left = a.snap_chunks;
@@ -374,8 +388,8 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
         // the warp below reads the top row up to column 32*nlc + 3: repeat the frozen last value (P[bottom row][m]) over the three
         // groups that follow this warp's last quad
         const int v = __shfl_sync(kFull, st.h[R - 1], 31);
-        if (cons_seen < nlc - 5) cons_seen = spin_until_ge(hand.cons_in_s, nlc - 5);
-        if (lane < 24) stc_volatile4(hand.next_rin_s + 4u * (unsigned)((32 * nlc + 4 * lane) & (VR - 1)), v, v, v, v);
+        if (cons_seen < nlc - 5) cons_seen = spin_until_ge(hand.cons_in_g, nlc - 5);
+        if (lane < 24) stg_quad(hand.next_rin_g + ((32 * nlc + 4 * lane) & (VR - 1)), v, v, v, v);
     }
     if (with_mid && lane < SHM) st_relaxed64(mid_out_p, pack_tagged(lds_volatile1(rmid_s + tog + 4u * (unsigned)(32 - SHM + lane)), a.tag));
     if (a.dbg && lane == 0 && q == 0) { a.dbg[4 * b + 2] = globaltimer_ns(); a.dbg[4 * b + 3] = spins; }
@@ -428,7 +442,6 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
         // Order: F0, then for k >= 1: F(k) followed by the map units of fill unit k-1, finally the map units of the last fill unit.
         __shared__ int s_ticket;
         __shared__ int s_cons[WARPS + 1];       // [WARPS]: INT_MAX, the "consumer" of a warp that feeds nobody
-        const unsigned sink_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)WARPS * SC::warp_smem_bytes(a.S));      // VR ints
         const unsigned CL = cluster_size(), crank = cluster_rank();
         const int per_unit = (int)CL * WARPS;
         const int nG = (a.nb + per_unit - 1) / per_unit;
@@ -467,14 +480,14 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
                     const bool last_of_unit = (w + 1 == WARPS) && (crank + 1 == CL);
                     const bool below = !last_of_unit && (b + 1 < a.nb);
                     if (!below) {
-                        hand.next_rin_s = map_to_cta(sink_s, crank);
-                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[WARPS]), crank);
+                        hand.next_rin_g = reinterpret_cast<int*>(smem_raw + (size_t)WARPS * SC::warp_smem_bytes(a.S));      // the sink
+                        hand.cons_in_g = &s_cons[WARPS];
                     } else if (w + 1 < WARPS) {
-                        hand.next_rin_s = map_to_cta((unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin), crank);
-                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[w + 1]), crank);
+                        hand.next_rin_g = WarpSmem<R, K>(warp_smem + SC::warp_smem_bytes(a.S), a.S).rin;
+                        hand.cons_in_g = &s_cons[w + 1];
                     } else {                            // warp 0 of the next CTA of the cluster (same layout: my own warp 0's addresses, mapped)
-                        hand.next_rin_s = map_to_cta((unsigned)__cvta_generic_to_shared(WarpSmem<R, K>(smem_raw, a.S).rin), crank + 1);
-                        hand.cons_in_s = map_to_cta((unsigned)__cvta_generic_to_shared(&s_cons[0]), crank + 1);
+                        hand.next_rin_g = map_generic_to_cta(WarpSmem<R, K>(smem_raw, a.S).rin, crank + 1);
+                        hand.cons_in_g = map_generic_to_cta(&s_cons[0], crank + 1);
                     }
                     fill_unit<R, K, 3>(a, warp_smem, sp_tab, b, lane, half_map, hand);
                 }
@@ -531,7 +544,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_fill_kernel(const FillArgs a)
             }
             t = (t + 1) >> 1;                                 // tickets 0, 1, 3, 5, ... are the fill units of bands 0, 1, 2, 3, ...
         }
-        fill_unit<R, K, 0>(a, warp_smem, sp_tab, t, lane, half_map, Handoff{0u, false, 0u, 0u, 0u});
+        fill_unit<R, K, 0>(a, warp_smem, sp_tab, t, lane, half_map, Handoff{0u, false, 0u, nullptr, nullptr});
         __syncwarp();
     }
 }

@@ -37,6 +37,11 @@ namespace nwb {
 
 constexpr int kPadL = 64;     // elements of padding in front of every header row (columns -64..-1 are scratch)
 
+// Per-warp block of "constants" in shared memory (fill, grouped mode): the four byte selectors of IDP.4A, -1, and a per-lane mask
+// that is -1 in lane 31.  They are LOADED at the top of every chunk: behind each wait loop of the unrolled chunk ptxas otherwise
+// re-materialises them (4 IMAD.MOV, and S2R + LOP3 + ISETP for the lane-31 predicate, per loop), which a lone warp pays in full.
+constexpr int kConstInts = 48;      // [0..3] selectors, [4] -1, [8 + lane] last-lane mask
+
 template <int R, int K>
 struct Sched {
     static_assert(R == 2 || R == 4 || R == 8 || R == 16, "rows per lane");
@@ -59,7 +64,7 @@ struct Sched {
     __host__ __device__ static constexpr size_t prof_bytes(int S) { return (size_t)(S + 1) * LSTRIDE; }
     __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
     {
-        return (prof_bytes(S) + (size_t)VR * 4 + 128 * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
+        return (prof_bytes(S) + (size_t)VR * 4 + 128 * 4 + kConstInts * 4 + (size_t)(XR + XM) * 2 + 15) & ~(size_t)15;
     }
 };
 
@@ -83,6 +88,7 @@ struct WarpSmem {
     int* rin;                // [VR] top-row ring: P[top][c] at (c & (VR-1))
     int* rout;               // [64] bottom-row staging: chunk lc, step s at ((lc & 1) * 32 + s)
     int* rmid;               // [64] the same for the band's MIDDLE row (bottom row of lane 15), see nw_fill.cuh
+    int* kconst;             // [kConstInts] see above
     unsigned short* xs;      // [XR + XM] letter ring: profile byte offset (letter * LSTRIDE) of column c at (c & (XR-1))
     __device__ __forceinline__ WarpSmem(unsigned char* base, int S)
     {
@@ -90,7 +96,8 @@ struct WarpSmem {
         rin = reinterpret_cast<int*>(base + SC::prof_bytes(S));
         rout = rin + SC::VR;
         rmid = rout + 64;
-        xs = reinterpret_cast<unsigned short*>(rmid + 64);
+        kconst = rmid + 64;
+        xs = reinterpret_cast<unsigned short*>(kconst + kConstInts);
     }
     __device__ __forceinline__ void put_letter(int c, unsigned off16)
     {
@@ -172,13 +179,14 @@ struct ChunkIO {
     // ---- grouped fill (HAND != 0): the header row crosses the warps of a CTA through a ring of quads in shared memory.
     // A quad is written by ONE 16-byte store and is its own ready flag: P >= 0 everywhere, the last word of an empty slot is -1.
     unsigned hin_s;                  // HAND & 1: shared-space byte address of quad 1 of this chunk in this warp's ring (quad j at + 16*(j-1))
-    unsigned hout_s;                 // HAND & 2: cluster-window byte address of the ring of the warp below at position (32*lc) & (VR-1)
+    int* hout_p;                     // HAND & 2: generic pointer (possibly into another CTA of the cluster) to the ring of the warp below at position (32*lc) & (VR-1)
     bool hout_on;                    // HAND & 2: this chunk's quads are read by the warp below (false in the first chunk(s): columns < 0)
     // ---- HAND & 4: the fill's chunk loop hands over shared-space byte addresses (it keeps them as running values: a chunk loop
     // written with pointers into the shared window makes ptxas rebuild window bases and 64-bit products in every iteration)
     unsigned xs_s, prof_s;           // = xs_lane, prof_lane
     unsigned rin_s, rin_next_s;      // = rin_chunk, rin_next
     unsigned rout_s, rmid_s;         // = rout_chunk, rmid_chunk (0 = keep nothing)
+    unsigned kconst_s;               // the warp's constant block (HAND & 3 only)
 };
 
 __device__ __forceinline__ int4 lds_volatile4(unsigned addr)
@@ -193,9 +201,18 @@ __device__ __forceinline__ void sts_volatile4(unsigned addr, int a, int b, int c
 }
 // the same through the cluster window: `addr` comes from mapa (the ring / counter of a warp in ANOTHER CTA of the thread-block
 // cluster, or in this one -- a CTA's own shared memory is part of the window)
-__device__ __forceinline__ void stc_volatile4(unsigned addr, int a, int b, int c, int d)
+// A quad into a ring that may live in ANOTHER CTA of the thread-block cluster: a plain store through a GENERIC pointer (mapa.u64).
+// (st.shared::cluster with a 32-bit window address is lowered to the same generic store, but ptxas then rebuilds the 64-bit
+// address -- S2R SR_SWINHI + two moves -- in front of every single store.)
+__device__ __forceinline__ void stg_quad(int* p, int a, int b, int c, int d)
 {
-    asm volatile("st.volatile.shared::cluster.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+    asm volatile("st.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ int* map_generic_to_cta(int* p, unsigned cta_rank)
+{
+    unsigned long long r;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"((unsigned long long)p), "r"(cta_rank));
+    return reinterpret_cast<int*>(r);
 }
 __device__ __forceinline__ int ldc_volatile1(unsigned addr)
 {
@@ -265,6 +282,15 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
     constexpr int WPL = SC::WPL;
     const int src_lane = (lane + 31) & 31;
     const bool last = (lane == 31);
+    // grouped fill: selectors, -1 and the last-lane mask come from shared memory (see kConstInts)
+    constexpr bool KC = (HAND & 3) != 0;
+    int4 selq = make_int4(1, 1 << 8, 1 << 16, 1 << 24);
+    int minus1 = -1, lastmask = 0;
+    if constexpr (KC) {
+        selq = lds_volatile4(io.kconst_s);
+        minus1 = lds_volatile1(io.kconst_s + 16u);
+        lastmask = lds_volatile1(io.kconst_s + 32u + 4u * (unsigned)lane);
+    }
     // A single warp can issue a shared-memory / shuffle instruction only every ~5-6 clk (measured: LDS.32 20 thread-ops/clk/SM
     // at one warp per SM sub-partition, profiles/microbench_r1.jsonl), and that -- not the DPX chain -- bounds the step of a
     // lone warp.  So the loads are widened: letter offsets two steps per LDS.32 (K == 2: the lane's ring position is even),
@@ -353,7 +379,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
 #pragma unroll
                     for (int q = 0; q < QG - 1; q++) qq[q] = lds_volatile4(io.hin_s + 16u * (j0 - 1 + q));
                 }
-                sts_volatile1(alast + 12u, -1);
+                sts_volatile1(alast + 12u, minus1);
 #pragma unroll
                 for (int q = 0; q < QG; q++) {
                     const int e0 = 4 * (j0 + q) - L4;
@@ -374,7 +400,8 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
             if constexpr (MODE == 1) oup = __shfl_sync(kFull, last ? io.org0 + s : st.o[R - 1], src_lane);
         } else {
             up = st.up_next;
-            st.up_next = __shfl_sync(kFull, last ? rvs : st.h[R - 1], src_lane);     // consumed at step s+1
+            if constexpr (KC) st.up_next = __shfl_sync(kFull, (st.h[R - 1] & ~lastmask) | (rvs & lastmask), src_lane);
+            else st.up_next = __shfl_sync(kFull, last ? rvs : st.h[R - 1], src_lane);     // consumed at step s+1
             if constexpr (MODE == 1) {
                 oup = st.oup_next;
                 st.oup_next = __shfl_sync(kFull, last ? io.org0 + s + 1 : st.o[R - 1], src_lane);
@@ -387,7 +414,8 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int left = st.h[r];
-            const int t = add_byte(pw[s][r >> 2], 1u << (8 * (r & 3)), diag);
+            const unsigned selr = (r & 3) == 0 ? (unsigned)selq.x : (r & 3) == 1 ? (unsigned)selq.y : (r & 3) == 2 ? (unsigned)selq.z : (unsigned)selq.w;
+            const int t = add_byte(pw[s][r >> 2], KC ? selr : (1u << (8 * (r & 3))), diag);
             const int nv = max3(t, up, left);
             if constexpr (MODE == 3) io.dump_lane[(long long)r * io.dump_ld + s] = nv;
             if constexpr (MODE == 1 || MODE == 2) {
@@ -425,7 +453,7 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
                 }
             }
             if constexpr (HOUT) {      // ... and straight into the ring of the warp below: one quad per four steps
-                if ((s & 3) == 3 && last && io.hout_on) stc_volatile4(io.hout_s + 4u * (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
+                if ((s & 3) == 3 && last && io.hout_on) stg_quad(io.hout_p + (s - 3), outv[s - 3], outv[s - 2], outv[s - 1], outv[s]);
             }
         }
         if constexpr (MODE == 1) {
