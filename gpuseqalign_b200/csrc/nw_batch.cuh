@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
     constexpr int By = SC::By, PD = SC::PD, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned sp_tab[kSpWords];
-    stage_sprime(sp_tab, a.sprime, a.S);
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;

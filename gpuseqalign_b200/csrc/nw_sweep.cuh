@@ -111,12 +111,35 @@ struct WarpSmem {
 // of a warp read the same column group of 32 different rows), row S is all zero (padding rows).
 constexpr int kSpPitch = 17;                              // words per row
 constexpr int kSpWords = (kMaxLetters + 1) * kSpPitch;    // static shared memory of every kernel that builds profiles
-__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S)
+// The S*S byte table arrives with ONE bulk copy of the TMA engine (cp.async.bulk global -> shared, completion on an mbarrier)
+// into `landing` -- any 16-byte aligned shared memory of >= S*S + 15 bytes that the caller does not use yet (every kernel passes
+// the start of its dynamic shared memory) -- and is then spread into the padded rows.  (The letters themselves are consumed 32
+// bytes per chunk and warp, at arbitrary alignment: below the granularity of a bulk copy; they stay on the LDG path.)
+__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S, unsigned char* landing)
 {
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const unsigned bytes = ((unsigned)(S * S) + 15u) & ~15u;           // the device buffer is allocated with slack (nwb200_set_scoring)
+    const unsigned mbar = (unsigned)__cvta_generic_to_shared(&s_mbar), dst = (unsigned)__cvta_generic_to_shared(landing);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     for (int i = threadIdx.x; i < kSpWords; i += blockDim.x) sp_tab[i] = 0u;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(sprime), "r"(bytes), "r"(mbar) : "memory");
+    }
+    unsigned done = 0, polls = 0;
+    while (!done) {                                                      // phase 0 of the one-shot barrier
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], 0;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(done) : "r"(mbar) : "memory");
+        if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
+    }
     unsigned char* t = reinterpret_cast<unsigned char*>(sp_tab);
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) t[(i / S) * (kSpPitch * 4) + (i % S)] = __ldg(sprime + i);
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) t[(i / S) * (kSpPitch * 4) + (i % S)] = landing[i];
     __syncthreads();
 }
 

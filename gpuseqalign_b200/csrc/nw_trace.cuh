@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     constexpr int By = SC::By, LAG = SC::LAG, PD = SC::PD, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned sp_tab[kSpWords];
-    stage_sprime(sp_tab, a.sprime, a.S);
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int m = a.m, nlc = SC::nlc(m);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
     constexpr int DB = R / 4;                                  // bytes of move codes per lane and step
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned sp_tab[kSpWords];
-    stage_sprime(sp_tab, a.sprime, a.S);
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x;
     WarpSmem<R, K> sm(smem_raw, a.S);
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_dump_kernel(const DumpArgs a)
     constexpr int By = SC::By, PD = SC::PD, VR = SC::VR, XR = SC::XR;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned sp_tab[kSpWords];
-    stage_sprime(sp_tab, a.sprime, a.S);
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
     const int m = a.m, nlc = SC::nlc(m);
