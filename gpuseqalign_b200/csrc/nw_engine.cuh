@@ -76,7 +76,8 @@ struct nwb200_ctx {
     bool pair_resident = false;
     bool headers_valid = false;
     bool fill_done = false;
-    nwb::DevBuf d_y, d_x, d_HR, d_snap, d_lastcol, d_sync;
+    nwb::DevBuf d_y, d_HR, d_snap, d_lastcol, d_sync;      // d_y: the row letters, then (at x_off) the column letters
+    size_t x_off = 0;
     nwb::PinBuf h_stage, h_small, h_trace;
     // traceback
     nwb::DevBuf d_map, d_MID, d_tmeta, d_ops, d_dense, d_export, d_HR2, d_cut;

@@ -41,7 +41,9 @@ struct TraceArgs {
     int* cnt;                        // [nb]   moves emitted by band b
     unsigned char* ops;              // per-band move lists, codes 0 '=', 1 'X', 2 'I', 3 'D'
     unsigned char* dense;            // packed backward move list
-    long long* total;                // [2]: total moves, consistency flag
+    long long* total;                // [4]: total moves, consistency flag, the fill's score element (tag | P), the engine's wait-timeout flag
+                                     // -- header of the dense list, so that ONE device-to-host copy brings everything a pair needs
+    const unsigned long long* score_elem;
     int map_half;                    // 1: map rows 2b (upper half of band b) and 2b+1 (lower half); 0: one map row per band
     // ---- segmented maps (nw_map_kernel): a band's map is computed in nseg independent column segments, every segment resuming
     // the sweep from a snapshot of the fill.  A path that leaves a segment through its LEFT cut carries the negative label
@@ -382,7 +384,11 @@ __global__ void __launch_bounds__(1024) nw_pack_kernel(const TraceArgs a)
         }
         __syncthreads();
     }
-    if (tid == 0) { a.total[0] = s_carry; a.total[1] = s_bad; }
+    if (tid == 0) {
+        a.total[0] = s_carry; a.total[1] = s_bad;
+        a.total[2] = (long long)ld_relaxed64(a.score_elem);
+        a.total[3] = (long long)g_wait_timeout;
+    }
 }
 
 

@@ -152,7 +152,7 @@ void nwb200_destroy(nwb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
-    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_x, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
+    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
                       &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
                       &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_dbg, &c->d_wave})
         b->release();
@@ -198,15 +198,18 @@ static int check_range(nwb200_ctx* c, long long n, long long m)
     return NWB200_SUCCESS;
 }
 
+static size_t stage_off_x(long long n) { return ((size_t)n + 63) & ~(size_t)63; }
+
 static int upload_common(nwb200_ctx* c, const uint8_t* stage_y, long long n, const uint8_t* stage_x, long long m, const nwb200_params* p)
 {
     int rc = plan_geometry(c, (int)n, (int)m, p);
     if (rc) return rc;
-    CU(c, c->d_y.ensure((size_t)n + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc y");
-    CU(c, c->d_x.ensure((size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc x");
+    // y and x live in ONE device buffer (x at x_off) and are staged the same way: one H2D copy per pair
+    c->x_off = stage_off_x(n);
+    if (stage_x != stage_y + c->x_off) return fail(c, NWB200_ERR_INVALID_VALUE, "internal: staging layout");
+    CU(c, c->d_y.ensure(c->x_off + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc letters");
     CU(c, cudaEventRecord(c->ev[0], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
-    CU(c, cudaMemcpyAsync(c->d_y.p, stage_y, (size_t)n, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D y");
-    CU(c, cudaMemcpyAsync(c->d_x.p, stage_x, (size_t)m, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D x");
+    CU(c, cudaMemcpyAsync(c->d_y.p, stage_y, c->x_off + (size_t)m, cudaMemcpyHostToDevice, c->stream), NWB200_ERR_MEMORY_TRANSFER, "H2D letters");
     CU(c, cudaEventRecord(c->ev[1], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     c->pair_resident = true; c->headers_valid = false; c->fill_done = false; c->trace_done = false;
     return NWB200_SUCCESS;
@@ -220,9 +223,9 @@ int nwb200_upload_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint
     int rc = check_range(c, n, m);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->stream), NWB200_ERR_CUDA_GENERAL, "sync before staging");
-    CU(c, c->h_stage.ensure((size_t)n + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
+    CU(c, c->h_stage.ensure(stage_off_x(n) + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
     uint8_t* sy = c->h_stage.as<uint8_t>();
-    uint8_t* sx = sy + n;
+    uint8_t* sx = sy + stage_off_x(n);
     const int S = c->S;
     unsigned bad = 0;
     for (int64_t i = 0; i < n; i++) { uint8_t v = y[i]; bad |= (v >= S); sy[i] = v; }
@@ -240,9 +243,9 @@ static int upload_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, 
     int rc = check_range(c, n, m);
     if (rc) return rc;
     CU(c, cudaStreamSynchronize(c->stream), NWB200_ERR_CUDA_GENERAL, "sync before staging");
-    CU(c, c->h_stage.ensure((size_t)n + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
+    CU(c, c->h_stage.ensure(stage_off_x(n) + (size_t)m + 64), NWB200_ERR_MEMORY_ALLOCATION, "alloc pinned staging");
     uint8_t* sy = c->h_stage.as<uint8_t>();
-    uint8_t* sx = sy + n;
+    uint8_t* sx = sy + stage_off_x(n);
     const unsigned S = (unsigned)c->S;
     unsigned bad = 0;
     for (int64_t i = 0; i < n; i++) { unsigned v = (unsigned)seqY[i + 1]; bad |= (v >= S); sy[i] = (uint8_t)v; }   // element 0 is the dummy header
@@ -269,7 +272,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     CU(c, cudaEventRecord(c->ev[2], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     CU(c, cudaMemsetAsync(c->d_sync.p, 0, sizeof(int) * 8, c->stream), NWB200_ERR_CUDA_GENERAL, "memset ticket");
     FillArgs a;
-    a.y = c->d_y.as<uint8_t>(); a.x = c->d_x.as<uint8_t>(); a.n = g.n; a.m = g.m;
+    a.y = c->d_y.as<uint8_t>(); a.x = (c->d_y.as<uint8_t>() + c->x_off); a.n = g.n; a.m = g.m;
     a.sprime = c->d_sprime.as<uint8_t>(); a.S = c->S;
     a.HR = c->d_HR.as<unsigned long long>(); a.ldr = g.ldr;
     a.snap = (keep && g.nsnap > 0) ? c->d_snap.as<int>() : nullptr;
@@ -321,14 +324,22 @@ int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
     cudaSetDevice(c->device);
     const Geometry& g = c->g;
     unsigned long long* hs = c->h_small.as<unsigned long long>();
-    // the score is the last real element of the bottom row of the last band
-    const unsigned long long* src = c->d_HR.as<unsigned long long>() + (long long)g.nb * g.ldr + kPadL + (g.m - 1);
-    CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
-    CU(c, cudaMemcpyAsync(hs, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
-    CU(c, cudaMemcpyAsync(hs + 1, c->d_timeout_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H wait flag");
-    CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    const bool with_moves = c->trace_done && c->moves_on_host;      // NWB200_WITH_TRACE: score element and wait flag arrive in the move list's header
+    if (!with_moves) {
+        // the score is the last real element of the bottom row of the last band
+        const unsigned long long* src = c->d_HR.as<unsigned long long>() + (long long)g.nb * g.ldr + kPadL + (g.m - 1);
+        CU(c, cudaEventRecord(c->ev[4], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+        CU(c, cudaMemcpyAsync(hs, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H score");
+        CU(c, cudaMemcpyAsync(hs + 1, c->d_timeout_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream), NWB200_ERR_MEMORY_TRANSFER, "D2H wait flag");
+        CU(c, cudaEventRecord(c->ev[5], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
+    }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel execution", e);
+    if (with_moves) {
+        const long long* hd = c->h_trace.as<long long>();
+        hs[0] = (unsigned long long)hd[2];
+        hs[1] = (unsigned long long)hd[3];
+    }
     if (*reinterpret_cast<const int*>(hs + 1) != 0) {
         int zero = 0;
         cudaMemcpyToSymbol(g_wait_timeout, &zero, sizeof(int));
@@ -339,7 +350,7 @@ int nwb200_fetch_score(nwb200_ctx* c, int32_t* align_cost)
     *align_cost = (int32_t)((long long)(int)(unsigned)hs[0] + ((long long)g.n + g.m) * c->gap);
     c->timing.align_cpy_dev = ev_ms(c->ev[0], c->ev[1]);
     c->timing.align_calc = ev_ms(c->ev[2], c->ev[3]);
-    c->timing.align_cpy_host = ev_ms(c->ev[4], c->ev[5]);
+    c->timing.align_cpy_host = with_moves ? ev_ms(c->ev[8], c->ev[9]) : ev_ms(c->ev[4], c->ev[5]);
     return NWB200_SUCCESS;
 }
 
