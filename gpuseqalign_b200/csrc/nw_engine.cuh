@@ -88,7 +88,7 @@ struct nwb200_ctx {
     bool inline_map = false;
     bool half_map = true;
     bool grouped = true;
-    int cluster_max = 8;             // largest thread-block cluster the grouped fill may use (1 = no cluster launch)
+    int cluster_max = 16;            // largest thread-block cluster the grouped fill may use (1 = no cluster launch)
     bool map_is_half = false;
     bool edit_cached = false;
     bool moves_on_host = false;      // the move list of the last traceback has been copied into h_trace already

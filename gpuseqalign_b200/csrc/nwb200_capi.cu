@@ -74,6 +74,12 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
         attr_set = smem;
     }
     cudaError_t e = cudaSuccess;
+    static bool nonportable = false;
+    if (cluster > 8 && !nonportable) {
+        e = cudaFuncSetAttribute(nw_fill_kernel<R, K, W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(non-portable cluster)", e);
+        nonportable = true;
+    }
     if (cluster > 1) {
         // thread-block clusters: the hand-off ring of the last warp of a CTA is the shared memory of the next CTA of its cluster
         cudaLaunchConfig_t cfg = {};
@@ -83,6 +89,11 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
         at[0].val.clusterDim.x = (unsigned)cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         e = cudaLaunchKernelEx(&cfg, nw_fill_kernel<R, K, W>, a);
+        if (e != cudaSuccess && cluster > 8) {      // a non-portable cluster that cannot be placed: the portable size always can
+            (void)cudaGetLastError();
+            at[0].val.clusterDim.x = 8;
+            e = cudaLaunchKernelEx(&cfg, nw_fill_kernel<R, K, W>, a);
+        }
     } else {
         nw_fill_kernel<R, K, W><<<grid, W * 32, smem, c->stream>>>(a);
         e = cudaGetLastError();
@@ -101,7 +112,7 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     int cluster = 1;
     if (a.grouped) {
         // cluster size: as many CTAs as a chain of bands can use, at most the portable 8
-        if (c->cluster_max > 1 && g.W == 4) cluster = g.nb > 16 ? 8 : (g.nb > 8 ? 4 : (g.nb > 4 ? 2 : 1));
+        if (c->cluster_max > 1 && g.W == 4) cluster = g.nb > 32 ? 16 : (g.nb > 16 ? 8 : (g.nb > 8 ? 4 : (g.nb > 4 ? 2 : 1)));
         if (cluster > c->cluster_max) cluster = c->cluster_max;
         const long long per = (long long)g.W * cluster;
         ctas_needed = (((long long)g.nb + per - 1) / per) * (1 + (a.map ? (a.map_half ? 2 : 1) : 0)) * cluster;
@@ -414,7 +425,7 @@ NWB200_API int nwb200_debug_band_stamps(nwb200_ctx* c, int enable, int mode, uns
     if (!c) return NWB200_ERR_INVALID_VALUE;
     c->dbg_stamps = (enable & 1) != 0; c->dbg_mode = mode;
     c->fuse_map = (enable & 4) == 0; c->inline_map = (enable & 8) != 0; c->half_map = (enable & 16) == 0; c->grouped = (enable & 32) == 0;
-    c->cluster_max = (enable & 64) ? 1 : ((enable & 128) ? 2 : ((enable & 256) ? 4 : 8));
+    c->cluster_max = (enable & 64) ? 1 : ((enable & 128) ? 2 : ((enable & 256) ? 4 : ((enable & 512) ? 8 : 16)));
     if (out && c->fill_done && c->d_dbg.p) {
         int nb = 3 * c->g.nb < max_bands ? 3 * c->g.nb : max_bands;
         cudaStreamSynchronize(c->stream);
