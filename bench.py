@@ -351,10 +351,10 @@ def main():
             "roofline": {"bound": "int-issue (DPX VIMNMX3, 1 per cell; not hbm/tensor)", "achieved": achieved, "peak": peak, "unit": "GCUPS",
                          "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
-                         # (profiles/r1x_ncu_fill_clusters_16k.txt: 38.5 MB for the 16k pair under the profiler's cold caches --
+                         # (profiles/r1y_ncu_fill_cluster16_16k.txt: 35.5 MB for the 16k pair under the profiler's cold caches --
                          # header rows, middle rows, origin maps and snapshots, 59 MB in all, live in L2 otherwise;
-                         # profiles/r1d_ncu_batch_*.txt: 546 B per pair)
-                         "traffic": (38534656 if (args.workload == "pair16k" and args.len == 16384 and with_trace) else
+                         # profiles/r1u_ncu_batch_*.txt: 543 B per pair)
+                         "traffic": (35489792 if (args.workload == "pair16k" and args.len == 16384 and with_trace) else
                                      (546.0 * per if args.workload == "batch256" else None)),
                          "kernel": "nw_fill_kernel" if args.workload == "pair16k" else "nw_batch_kernel", "kernel_ms": fill_ms,
                          "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
