@@ -295,7 +295,7 @@ __device__ __forceinline__ int4 ring_take(unsigned addr)
     sts_volatile1(addr + 12, -1);
     return v;
 }
-constexpr int kRingQG = 2;      // quads per readiness check of a hand-off ring (the producer's stores arrive in order: the last quad vouches for the others)
+constexpr int kRingQG = 2;      // quads per readiness check of a hand-off ring
 
 // One 32-step chunk of one warp.
 template <int R, int K, int MODE, bool TOP = true, int HAND = 0>
@@ -372,8 +372,8 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
     constexpr bool HIN = (HAND & 1) != 0, HOUT = (HAND & 2) != 0;
     static_assert(!HIN || TOP, "a hand-off ring feeds the top row");
     // HIN: quad j of the chunk = top-row elements 4j-L4 .. 4j-L4+3, first needed at step 4j-3 (both skews).  Quads are taken in
-    // groups of QG: the loads are issued one step before the first quad is needed and land (wait for the producer if the LAST quad
-    // of the group is still empty, then hand that slot back) right before use: the warp follows the warp above at a distance of
+    // groups of QG: the loads are issued one step before the first quad is needed and land (wait for the producer while a quad
+    // of the group is still empty, then hand the slots back) right before use: the warp follows the warp above at a distance of
     // one group.  Quad 0 is the previous chunk's quad 8, carried in registers.  (A check per quad costs more than it saves: every
     // wait loop inside the unrolled chunk makes ptxas rematerialise addresses and constants behind it.)
     constexpr int L4 = SC::L4, QG = kRingQG;
@@ -396,13 +396,18 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
                 for (int q = 0; q < QG; q++) qq[q] = lds_volatile4(io.hin_s + 16u * (s / 4 + q));
             } else if ((s & (4 * QG - 1)) == 1) {
                 const int j0 = (s + 3) / 4;                        // first quad of the group
-                const unsigned alast = io.hin_s + 16u * (j0 - 1 + QG - 1);
-                if (__any_sync(kFull, qq[QG - 1].w < 0)) {
-                    qq[QG - 1] = ring_wait(alast);
+                const unsigned a0 = io.hin_s + 16u * (j0 - 1);
+                // EVERY quad of the group is checked and handed back (not only the last one): stores into another CTA's shared
+                // memory are not promised to arrive in program order
+                int any_w = qq[0].w;
 #pragma unroll
-                    for (int q = 0; q < QG - 1; q++) qq[q] = lds_volatile4(io.hin_s + 16u * (j0 - 1 + q));
+                for (int q = 1; q < QG; q++) any_w |= qq[q].w;
+                if (__any_sync(kFull, any_w < 0)) {
+#pragma unroll
+                    for (int q = 0; q < QG; q++) qq[q] = ring_wait(a0 + 16u * q);
                 }
-                sts_volatile1(alast + 12u, minus1);
+#pragma unroll
+                for (int q = 0; q < QG; q++) sts_volatile1(a0 + 16u * q + 12u, minus1);
 #pragma unroll
                 for (int q = 0; q < QG; q++) {
                     const int e0 = 4 * (j0 + q) - L4;
