@@ -1,0 +1,175 @@
+// nw_batch2.cuh -- many independent short pairs, TWO pairs per warp in packed 16-bit halves (BASELINE config 3).
+//
+// Same systolic sweep as nw_batch.cuh (one band of 32*R rows per pair, lanes one column apart), but every register holds the
+// cell of pair A in its low and the cell of pair B in its high 16 bits, so that ONE DPX instruction (VIMNMX3.U16x2) and ONE
+// warp shuffle serve two cells.  In shifted coordinates P = H - (i+j)*gap >= 0 and P[i][j] <= min(i,j) * max(s'); with
+// s' <= 127 and min(i,j) <= 256 that is <= 32 512, so neither half overflows and the packed add never carries from the low
+// half into the high one.  (The host picks this kernel only when both bounds hold, nwb200_capi_batch.inc.)
+//
+// The two pairs have different row AND column letters, so the substitution term of a packed cell is two table lookups:
+//   pair A: byte r of a packed per-lane profile word, added to the LOW half with IDP.4A (selector byte = 1), as in nw_sweep.cuh
+//   pair B: byte r of a second per-lane profile word that holds 2*s', added to the HIGH half with IDP.2A: the 16-bit operand is
+//           the constant 32768 in the half that selects the byte (32768 * 2*s' = s' << 16), .LO / .HI pick the byte pair
+// Both adds run on the fma pipe, the packed 3-way max on the alu pipe: 3 instructions per 2 cells instead of 4.
+// Ragged pairs need no extra code: rows are aligned to the bottom of the band per pair (padding rows have zero profile bytes),
+// columns past the end of the shorter pair read the all-zero profile row and freeze that half.
+#pragma once
+#include "nw_batch.cuh"
+
+namespace nwb {
+
+template <int R>
+struct Sched2 {
+    static_assert(R == 4 || R == 8, "rows per lane");
+    static constexpr int By = 32 * R;
+    static constexpr int WA = R / 4;                   // words per lane and letter and pair (bytes: s' for pair A, 2*s' for pair B)
+    static constexpr int STRIDE = 128 * WA;            // bytes between the profile rows of two letters
+    static constexpr int LAG = 31;
+    static constexpr int PD = 2;                       // letter groups prefetched ahead
+    static constexpr int XR = 128, XM = 32;            // letter ring of (offset A, offset B) entries + mirror: a chunk reads columns
+                                                       // 32*lc-31 .. 32*lc+31 and columns up to 32*lc+95 are written ahead
+    __host__ __device__ static constexpr int nlc(int m) { return (m + LAG + 31) / 32; }
+    __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
+    {
+        return (size_t)(S + 1) * STRIDE * 2 + (size_t)(XR + XM) * 8;
+    }
+};
+
+constexpr int kBatch2MaxSprime = 127;      // 2 * s' must fit a byte, and 256 * s' must stay below 2^15
+
+template <int R, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a)
+{
+    using S2 = Sched2<R>;
+    constexpr int By = S2::By, WA = S2::WA, PD = S2::PD, XR = S2::XR, XM = S2::XM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned sp_tab[kSpWords];
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int S = a.S;
+    unsigned char* base = smem_raw + (size_t)w * S2::warp_smem_bytes(S);
+    WarpSmem<R, 1> smA(base, S), smB(base + (size_t)(S + 1) * S2::STRIDE, S);      // only .prof is used (build_profile)
+    uint2* ring = reinterpret_cast<uint2*>(base + (size_t)(S + 1) * S2::STRIDE * 2);  // [XR + XM]
+    const unsigned char* laneA = smA.prof + lane * 4 * WA;
+    const unsigned char* laneB = smB.prof + lane * 4 * WA;
+    const int src_lane = (lane + 31) & 31;
+    const bool last = lane == 31;
+
+    auto put_letters = [&](int c, unsigned la, unsigned lb) {
+        const int p = c & (XR - 1);
+        const uint2 v = make_uint2(la * S2::STRIDE, lb * S2::STRIDE);
+        ring[p] = v;
+        if (p < XM) ring[p + XR] = v;
+    };
+
+    for (;;) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.ticket, 1ull);
+        t = __shfl_sync(kFull, t, 0);
+        const unsigned long long pA = a.first + 2 * t, pB = pA + 1;
+        if (pA >= a.npairs) break;
+        const bool hasB = pB < a.npairs;
+        int nA = (int)a.lenY[pA], mA = (int)a.lenX[pA];
+        int nB = hasB ? (int)a.lenY[pB] : 0, mB = hasB ? (int)a.lenX[pB] : 0;
+        const int gapsA = (nA + mA) * a.gap, gapsB = (nB + mB) * a.gap;
+        const bool tallA = nA > By, tallB = nB > By;
+        if (tallA) { nA = 0; mA = 0; }                     // swept as an empty pair; the host re-runs it as a single pair
+        if (tallB) { nB = 0; mB = 0; }
+        if (nA == 0) mA = 0;
+        if (nB == 0) mB = 0;
+        const uint8_t* yA = a.letters + a.offY[pA];
+        const uint8_t* xA = a.letters + a.offX[pA];
+        const uint8_t* yB = a.letters + a.offY[hasB ? pB : pA];
+        const uint8_t* xB = a.letters + a.offX[hasB ? pB : pA];
+        const int m = max(mA, mB);
+        __syncwarp();
+        // ---- pair A: byte profile (shared code with the 32-bit kernels)
+        const int padA = By - nA, padB = By - nB;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane * R - padA + r;
+            if (i >= 0 && i < nA && (unsigned)__ldg(yA + i) >= (unsigned)S) *a.err = 1;
+        }
+        build_profile<R, 1>(smA, sp_tab, S, yA, (long long)lane * R - padA, nA, lane, nullptr);
+        // ---- pair B: the same layout with doubled bytes
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = lane * R - padB + r;
+            if (i >= 0 && i < nB && (unsigned)__ldg(yB + i) >= (unsigned)S) *a.err = 1;
+        }
+        build_profile<R, 1, 1>(smB, sp_tab, S, yB, (long long)lane * R - padB, nB, lane, nullptr);
+        // ---- letter ring: columns -32..-1 are outside (zero row), then PD groups ahead
+        auto fetch = [&](int c, unsigned& la, unsigned& lb) {
+            la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;
+            lb = c < mB ? (unsigned)__ldg(xB + c) : (unsigned)S;
+        };
+        auto check_put = [&](int c, unsigned la, unsigned lb) {
+            if (la > (unsigned)S) { la = (unsigned)S; *a.err = 1; }
+            if (lb > (unsigned)S) { lb = (unsigned)S; *a.err = 1; }
+            put_letters(c, la, lb);
+        };
+        put_letters(-32 + lane, (unsigned)S, (unsigned)S);      // (ZOFF for both pairs)
+        for (int g = 0; g < PD; g++) {
+            unsigned la, lb;
+            fetch(32 * g + lane, la, lb);
+            check_put(32 * g + lane, la, lb);
+        }
+        __syncwarp();
+        unsigned h[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) h[r] = 0u;
+        unsigned dprev = 0u;
+        const int nlc = S2::nlc(m);
+        for (int lc = 0; lc < nlc; lc++) {
+            const int cp = 32 * (lc + PD) + lane;
+            unsigned pf_a, pf_b;
+            fetch(cp, pf_a, pf_b);                                               // checked when it lands, after the chunk
+            const uint2* xs = ring + ((32 * lc - lane) & (XR - 1));
+            uint2 xo[32];
+            unsigned wa[32][WA], wb[32][WA];
+            auto load_xo = [&](int s) { if (s < 32) xo[s] = xs[s]; };
+            auto load_pw = [&](int s) {
+                if (s >= 32) return;
+                const unsigned char* qa = laneA + xo[s].x;
+                const unsigned char* qb = laneB + xo[s].y;
+                if constexpr (WA == 1) { wa[s][0] = *reinterpret_cast<const unsigned*>(qa); wb[s][0] = *reinterpret_cast<const unsigned*>(qb); }
+                else {
+                    const uint2 va = *reinterpret_cast<const uint2*>(qa), vb = *reinterpret_cast<const uint2*>(qb);
+                    wa[s][0] = va.x; wa[s][1] = va.y; wb[s][0] = vb.x; wb[s][1] = vb.y;
+                }
+            };
+#pragma unroll
+            for (int s = 0; s < 3; s++) load_xo(s);
+#pragma unroll
+            for (int s = 0; s < 2; s++) load_pw(s);
+#pragma unroll
+            for (int s = 0; s < 32; s++) {
+                load_xo(s + 3);
+                load_pw(s + 2);
+                // rotate-shuffle: the bottom row of the lane above; row 0 of P (above lane 0) is zero
+                unsigned up = __shfl_sync(kFull, last ? 0u : h[R - 1], src_lane);
+                unsigned diag = dprev;
+                dprev = up;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const unsigned left = h[r];
+                    unsigned tt = __dp4a(wa[s][r >> 2], 1u << (8 * (r & 3)), diag);                    // low half += s'_A
+                    const unsigned half = (r & 1) ? 0x80000000u : 0x00008000u;                          // 32768 * (2 s'_B) = s'_B << 16
+                    tt = (r & 2) ? __dp2a_hi(half, wb[s][r >> 2], tt) : __dp2a_lo(half, wb[s][r >> 2], tt);
+                    const unsigned nv = __vimax3_u16x2(tt, up, left);
+                    diag = left; up = nv; h[r] = nv;
+                }
+            }
+            __syncwarp();
+            check_put(cp, pf_a, pf_b);
+            __syncwarp();
+        }
+        // lane 31's last row is row n of both matrices, frozen behind their last columns: un-shift H = P + (n+m)*gap
+        if (last) {
+            a.scores[pA] = tallA ? kBatchTooTall : (int)(h[R - 1] & 0xffffu) + gapsA;
+            if (hasB) a.scores[pB] = tallB ? kBatchTooTall : (int)(h[R - 1] >> 16) + gapsB;
+        }
+    }
+}
+
+}  // namespace nwb

@@ -8,6 +8,7 @@
 #include "nw_fill.cuh"
 #include "nw_trace.cuh"
 #include "nw_batch.cuh"
+#include "nw_batch2.cuh"
 #include "nw_scan.cuh"
 
 using namespace nwb;

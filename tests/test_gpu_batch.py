@@ -93,3 +93,46 @@ def test_batch_pinned_and_pageable_sources_agree(engine, scoring, oracle):
     b = engine.align_batch(pinned, offY, lenY, offX, lenX)
     assert np.array_equal(a, b) and np.array_equal(a[:4000], exp)
     assert int(a.astype(np.int64).sum()) == int(b.astype(np.int64).sum())
+
+
+@pytest.mark.parametrize("n_pairs,max_y,max_x", [(1, 256, 256), (7, 128, 200), (601, 256, 300), (333, 100, 60)])
+def test_batch_packed_and_32bit_kernels_agree(engine, scoring, oracle, monkeypatch, n_pairs, max_y, max_x):
+    """Two pairs per warp in 16-bit halves (nw_batch2.cuh) vs one pair per warp (nw_batch.cuh) vs the oracle: odd pair
+    counts (a warp whose second half is empty), both band heights, ragged partners in one warp."""
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(1000 + n_pairs)
+    letters, offY, lenY, offX, lenX = _ragged(rng, n_pairs, max_y, max_x)
+    exp = oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11)
+    monkeypatch.setenv("NWB200_BATCH_PACKED", "1")
+    packed = engine.align_batch(letters, offY, lenY, offX, lenX)
+    monkeypatch.setenv("NWB200_BATCH_PACKED", "0")
+    plain = engine.align_batch(letters, offY, lenY, offX, lenX)
+    assert np.array_equal(packed, exp)
+    assert np.array_equal(plain, exp)
+
+
+def test_batch_packed_halves_at_their_bound(scoring, oracle):
+    """s' = 127 on the diagonal and identical 256-letter sequences: P reaches 256 * 127 = 32 512 in both halves of a register;
+    one notch more (s' = 128) must take the 32-bit kernel and still agree."""
+    from gpuseqalign_b200 import Engine
+    S = 25
+    rng = np.random.default_rng(77)
+    seqs = [rng.integers(0, 20, 256).astype(np.uint8) for _ in range(3)]
+    # pairs: (s0,s0) (s1,s1) identical; (s0,s1) unrelated; (s2,s2) with an empty partner in the last warp
+    pool = np.concatenate([seqs[0], seqs[0], seqs[1], seqs[1], seqs[0], seqs[1], seqs[2], seqs[2]])
+    offY = np.arange(0, 8, 2, dtype=np.uint64) * 256
+    offX = offY + 256
+    lenY = np.full(4, 256, dtype=np.uint32); lenX = lenY.copy()
+    for diag in (105, 106):
+        subst = rng.integers(-4, 4, (S, S)).astype(np.int32)
+        subst = ((subst + subst.T) // 2).astype(np.int32)
+        np.fill_diagonal(subst, diag)
+        e = Engine(0)
+        try:
+            e.set_scoring(subst.ravel(), -11)
+            got = e.align_batch(pool, offY, lenY, offX, lenX)
+        finally:
+            e.close()
+        exp = oracle.score_batch(pool, offY, lenY, offX, lenX, subst.ravel(), -11)      # the oracle takes the flat S*S table
+        assert np.array_equal(got, exp), diag
+        assert got[0] == 256 * diag

@@ -30,6 +30,8 @@ enum Op {
     OP_SHFL, OP_LDS32, OP_LDS64, OP_LDS128,
     OP_MIX_MAX3_SHFL,      // 4x (imad+max3) + 1 shfl
     OP_MIX_MAX3_LDS,       // 4x (imad+max3) + 1 lds32
+    OP_DP2A,               // IDP.2A.LO.U16.U8
+    OP_MIX_PACKED2,        // two pairs per register: d = dp4a(wA, sel, diag) ; d = dp2a(wB, sel2, d) ; c = vimax3_u16x2(d, up, left)
     OP_COUNT
 };
 
@@ -39,7 +41,8 @@ static const char* op_names[OP_COUNT] = {
     "mix: IMAD+VIMNMX3 (per cell)", "mix: IDP4A+VIMNMX3 (per cell)", "mix: VIADDMNMX+VIMNMX (per cell)",
     "mix16: PRMT+VIADDMNMX16+VIMNMX16 (per 2 cells)", "mix16: VIADDMNMX16+VIMNMX16 (per 2 cells)",
     "SHFL.UP", "LDS.32", "LDS.64", "LDS.128",
-    "mix: 4x(IMAD+VIMNMX3)+SHFL (per 4 cells)", "mix: 4x(IMAD+VIMNMX3)+LDS32 (per 4 cells)"};
+    "mix: 4x(IMAD+VIMNMX3)+SHFL (per 4 cells)", "mix: 4x(IMAD+VIMNMX3)+LDS32 (per 4 cells)",
+    "IDP.2A", "mix16: IDP4A+IDP2A+VIMNMX3.U16x2 (per 2 cells)"};
 
 // "units" per inner-loop body per accumulator (what the reported rate counts).
 template <int OP>
@@ -55,6 +58,13 @@ __device__ __forceinline__ void body(int (&a)[ILP], int (&b)[ILP], int p, int q,
         else if (OP == OP_IMAD) a[k] = a[k] * p + q;
         else if (OP == OP_DP4A) a[k] = __dp4a(b[k], sel, a[k]);
         else if (OP == OP_PRMT) a[k] = __byte_perm(a[k], b[k], sel);
+        else if (OP == OP_DP2A) a[k] = __dp2a_lo((unsigned)b[k], (unsigned)sel, (unsigned)a[k]);
+        else if (OP == OP_MIX_PACKED2) {
+            unsigned d = __dp4a((unsigned)p, (unsigned)sel, (unsigned)b[k]);
+            d = __dp2a_lo((unsigned)q, (unsigned)sel, d);
+            unsigned c = __vimax3_u16x2(d, (unsigned)a[k], (unsigned)b[k]);
+            b[k] = a[k]; a[k] = c;
+        }
         else if (OP == OP_IADD) { asm volatile("add.s32 %0, %0, %1;" : "+r"(a[k]) : "r"(b[k])); }
         else if (OP == OP_LOP3) { asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[k]) : "r"(b[k]), "r"(p)); }
         else if (OP == OP_MIX_IMAD_MAX3) {
@@ -210,6 +220,8 @@ int main() {
         run_tp<OP_LDS128>(d_out, d_cyc, sms, threads, ILP, "ops");
         run_tp<OP_MIX_MAX3_SHFL>(d_out, d_cyc, sms, threads, 8, "cells");
         run_tp<OP_MIX_MAX3_LDS>(d_out, d_cyc, sms, threads, 8, "cells");
+        run_tp<OP_DP2A>(d_out, d_cyc, sms, threads, ILP, "ops");
+        run_tp<OP_MIX_PACKED2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
     }
     run_lat<OP_VIMNMX3>(d_out, d_cyc);
     run_lat<OP_VIADDMNMX>(d_out, d_cyc);
