@@ -37,9 +37,21 @@ struct Sched2 {
 
 constexpr int kBatch2MaxSprime = 127;      // 2 * s' must fit a byte, and 256 * s' must stay below 2^15
 
-template <int R, int WARPS>
+__device__ __forceinline__ unsigned prmt_generic(unsigned a, unsigned b, unsigned sel)
+{
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+// NP: the last NP rows of a lane (whole profile words) take the substitution term through the alu pipe instead of the fma pipe:
+// ONE byte permute builds (s'_A, 0, s'_B, 0) from the two profile words (selector nibbles with bit 3 set replicate the sign bit of
+// a byte, which is 0 for s' <= 127), one IADD3 adds it.  The words of those rows hold plain s' for pair B as well.
+template <int R, int WARPS, int NP = 0>
 __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a)
 {
+    static_assert(NP % 4 == 0 && NP <= R, "whole profile words");
+    constexpr int SHLB = ((1 << ((R - NP) / 4)) - 1);          // words of pair B that are stored doubled (IDP.2A rows)
     using S2 = Sched2<R>;
     constexpr int By = S2::By, WA = S2::WA, PD = S2::PD, XR = S2::XR, XM = S2::XM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -50,8 +62,9 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
     unsigned char* base = smem_raw + (size_t)w * S2::warp_smem_bytes(S);
     WarpSmem<R, 1> smA(base, S), smB(base + (size_t)(S + 1) * S2::STRIDE, S);      // only .prof is used (build_profile)
     uint2* ring = reinterpret_cast<uint2*>(base + (size_t)(S + 1) * S2::STRIDE * 2);  // [XR + XM]
-    const unsigned char* laneA = smA.prof + lane * 4 * WA;
-    const unsigned char* laneB = smB.prof + lane * 4 * WA;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const unsigned laneA_s = (unsigned)__cvta_generic_to_shared(smA.prof) + lane * 4 * WA;
+    const unsigned laneB_s = (unsigned)__cvta_generic_to_shared(smB.prof) + lane * 4 * WA;
     const int src_lane = (lane + 31) & 31;
     const bool last = lane == 31;
 
@@ -97,7 +110,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
             const int i = lane * R - padB + r;
             if (i >= 0 && i < nB && (unsigned)__ldg(yB + i) >= (unsigned)S) *a.err = 1;
         }
-        build_profile<R, 1, 1>(smB, sp_tab, S, yB, (long long)lane * R - padB, nB, lane, nullptr);
+        build_profile<R, 1, SHLB>(smB, sp_tab, S, yB, (long long)lane * R - padB, nB, lane, nullptr);
         // ---- letter ring: columns -32..-1 are outside (zero row), then PD groups ahead
         auto fetch = [&](int c, unsigned& la, unsigned& lb) {
             la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;
@@ -124,18 +137,24 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
             const int cp = 32 * (lc + PD) + lane;
             unsigned pf_a, pf_b;
             fetch(cp, pf_a, pf_b);                                               // checked when it lands, after the chunk
-            const uint2* xs = ring + ((32 * lc - lane) & (XR - 1));
+            // The loads are volatile asm with shared-space addresses so that they stay where they are written: the letter offsets
+            // three steps and the profile words two steps ahead of their use (left to itself the compiler sinks the profile loads
+            // to one step ahead to save registers, and every step then waits for shared memory).
+            const unsigned xs_s = ring_s + 8u * (unsigned)((32 * lc - lane) & (XR - 1));
             uint2 xo[32];
             unsigned wa[32][WA], wb[32][WA];
-            auto load_xo = [&](int s) { if (s < 32) xo[s] = xs[s]; };
+            auto load_xo = [&](int s) {
+                if (s < 32) asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(xo[s].x), "=r"(xo[s].y) : "r"(xs_s + 8u * (unsigned)s));
+            };
             auto load_pw = [&](int s) {
                 if (s >= 32) return;
-                const unsigned char* qa = laneA + xo[s].x;
-                const unsigned char* qb = laneB + xo[s].y;
-                if constexpr (WA == 1) { wa[s][0] = *reinterpret_cast<const unsigned*>(qa); wb[s][0] = *reinterpret_cast<const unsigned*>(qb); }
-                else {
-                    const uint2 va = *reinterpret_cast<const uint2*>(qa), vb = *reinterpret_cast<const uint2*>(qb);
-                    wa[s][0] = va.x; wa[s][1] = va.y; wb[s][0] = vb.x; wb[s][1] = vb.y;
+                const unsigned qa = laneA_s + xo[s].x, qb = laneB_s + xo[s].y;
+                if constexpr (WA == 1) {
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wa[s][0]) : "r"(qa));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wb[s][0]) : "r"(qb));
+                } else {
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wa[s][0]), "=r"(wa[s][1]) : "r"(qa));
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(wb[s][0]), "=r"(wb[s][1]) : "r"(qb));
                 }
             };
 #pragma unroll
@@ -153,9 +172,17 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
 #pragma unroll
                 for (int r = 0; r < R; r++) {
                     const unsigned left = h[r];
-                    unsigned tt = __dp4a(wa[s][r >> 2], 1u << (8 * (r & 3)), diag);                    // low half += s'_A
-                    const unsigned half = (r & 1) ? 0x80000000u : 0x00008000u;                          // 32768 * (2 s'_B) = s'_B << 16
-                    tt = (r & 2) ? __dp2a_hi(half, wb[s][r >> 2], tt) : __dp2a_lo(half, wb[s][r >> 2], tt);
+                    unsigned tt;
+                    if (r < R - NP) {
+                        tt = __dp4a(wa[s][r >> 2], 1u << (8 * (r & 3)), diag);                          // low half += s'_A
+                        const unsigned half = (r & 1) ? 0x80000000u : 0x00008000u;                      // 32768 * (2 s'_B) = s'_B << 16
+                        tt = (r & 2) ? __dp2a_hi(half, wb[s][r >> 2], tt) : __dp2a_lo(half, wb[s][r >> 2], tt);
+                    } else {
+                        constexpr unsigned j = 0;
+                        const unsigned jj = (unsigned)(r & 3) + j;
+                        const unsigned sel = jj | ((8u | jj) << 4) | ((4u + jj) << 8) | ((8u | (4u + jj)) << 12);
+                        tt = diag + prmt_generic(wa[s][r >> 2], wb[s][r >> 2], sel);
+                    }
                     const unsigned nv = __vimax3_u16x2(tt, up, left);
                     diag = left; up = nv; h[r] = nv;
                 }

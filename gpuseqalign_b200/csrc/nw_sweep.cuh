@@ -147,7 +147,7 @@ __device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __
 // the all-zero row used outside the sequence.  Four table rows (one per matrix row) are read a word (4 letters) at a
 // time and transposed with byte permutes: 16 instructions per 4 letters and 4 rows.
 // yrow0 = 0-based index into y of this lane's first row (negative / >= n: padding row, zero bytes).
-// SHL: every byte is stored shifted left by SHL bits (the packed batch kernel keeps 2*s' for its second pair; bytes must stay < 256).
+// SHL: bit q set = the bytes of word q are stored doubled (the packed batch kernel keeps 2*s' for its second pair; s' <= 127 there).
 template <int R, int K, int SHL = 0>
 __device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const unsigned* __restrict__ sp_tab, int S,
                                               const uint8_t* __restrict__ y, long long yrow0, long long n, int lane, unsigned* yl_out)
@@ -177,10 +177,10 @@ __device__ __forceinline__ void build_profile(const WarpSmem<R, K>& sm, const un
             const unsigned o0 = __byte_perm(t0, t1, 0x5410), o1 = __byte_perm(t0, t1, 0x7632);
             const unsigned o2 = __byte_perm(t2, t3, 0x5410), o3 = __byte_perm(t2, t3, 0x7632);
             const int xl = 4 * g4;
-            pl[(size_t)(xl + 0) * 32 * WPL + q] = o0 << SHL;
-            if (xl + 1 < S) pl[(size_t)(xl + 1) * 32 * WPL + q] = o1 << SHL;
-            if (xl + 2 < S) pl[(size_t)(xl + 2) * 32 * WPL + q] = o2 << SHL;
-            if (xl + 3 < S) pl[(size_t)(xl + 3) * 32 * WPL + q] = o3 << SHL;
+            pl[(size_t)(xl + 0) * 32 * WPL + q] = o0 << ((SHL >> q) & 1);
+            if (xl + 1 < S) pl[(size_t)(xl + 1) * 32 * WPL + q] = o1 << ((SHL >> q) & 1);
+            if (xl + 2 < S) pl[(size_t)(xl + 2) * 32 * WPL + q] = o2 << ((SHL >> q) & 1);
+            if (xl + 3 < S) pl[(size_t)(xl + 3) * 32 * WPL + q] = o3 << ((SHL >> q) & 1);
         }
         pl[(size_t)S * 32 * WPL + q] = 0u;
     }
