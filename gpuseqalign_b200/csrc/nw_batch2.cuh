@@ -37,6 +37,78 @@ struct Sched2 {
 
 constexpr int kBatch2MaxSprime = 127;      // 2 * s' must fit a byte, and 256 * s' must stay below 2^15
 
+// Both packed byte profiles of a warp's two pairs in ONE pass over the letters: prof[letter][lane][q] = bytes s'(y[row 4q..4q+3], letter)
+// (layout of build_profile, nw_sweep.cuh).  All 2R row letters are fetched up front (one global round trip), the words of a lane go
+// out as one 8-byte store, and the two independent transposes interleave.  SHLB: bit q set = pair B's word q is stored doubled.
+template <int R, int SHLB>
+__device__ __forceinline__ void build_profiles2(unsigned char* profA_lane, unsigned char* profB_lane, const unsigned* __restrict__ sp_tab, int S,
+                                                const uint8_t* __restrict__ yA, int i0A, int nA,
+                                                const uint8_t* __restrict__ yB, int i0B, int nB, int* err)
+{
+    constexpr int WA = R / 4;
+    constexpr unsigned STRIDE = 128 * WA;
+    unsigned ya[R], yb[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int ia = i0A + r, ib = i0B + r;
+        ya[r] = (ia >= 0 && ia < nA) ? (unsigned)__ldg(yA + ia) : (unsigned)S;
+        yb[r] = (ib >= 0 && ib < nB) ? (unsigned)__ldg(yB + ib) : (unsigned)S;
+    }
+    const unsigned* rowA[R];
+    const unsigned* rowB[R];
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        if (ya[r] > (unsigned)S) { ya[r] = (unsigned)S; bad = true; }
+        if (yb[r] > (unsigned)S) { yb[r] = (unsigned)S; bad = true; }
+        rowA[r] = sp_tab + ya[r] * kSpPitch;
+        rowB[r] = sp_tab + yb[r] * kSpPitch;
+    }
+    if (bad) *err = 1;
+#pragma unroll 1
+    for (int g4 = 0; 4 * g4 < S; g4++) {
+        unsigned oa[WA][4], ob[WA][4];
+#pragma unroll
+        for (int q = 0; q < WA; q++) {
+            {
+                const unsigned w0 = rowA[4 * q][g4], w1 = rowA[4 * q + 1][g4], w2 = rowA[4 * q + 2][g4], w3 = rowA[4 * q + 3][g4];
+                const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                const unsigned t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                oa[q][0] = __byte_perm(t0, t1, 0x5410); oa[q][1] = __byte_perm(t0, t1, 0x7632);
+                oa[q][2] = __byte_perm(t2, t3, 0x5410); oa[q][3] = __byte_perm(t2, t3, 0x7632);
+            }
+            {
+                const unsigned w0 = rowB[4 * q][g4], w1 = rowB[4 * q + 1][g4], w2 = rowB[4 * q + 2][g4], w3 = rowB[4 * q + 3][g4];
+                const unsigned t0 = __byte_perm(w0, w1, 0x5140), t1 = __byte_perm(w2, w3, 0x5140);
+                const unsigned t2 = __byte_perm(w0, w1, 0x7362), t3 = __byte_perm(w2, w3, 0x7362);
+                const int sh = (SHLB >> q) & 1;
+                ob[q][0] = __byte_perm(t0, t1, 0x5410) << sh; ob[q][1] = __byte_perm(t0, t1, 0x7632) << sh;
+                ob[q][2] = __byte_perm(t2, t3, 0x5410) << sh; ob[q][3] = __byte_perm(t2, t3, 0x7632) << sh;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const unsigned xl = 4u * (unsigned)g4 + (unsigned)j;
+            if (xl < (unsigned)S) {
+                if constexpr (WA == 2) {
+                    *reinterpret_cast<uint2*>(profA_lane + xl * STRIDE) = make_uint2(oa[0][j], oa[1][j]);
+                    *reinterpret_cast<uint2*>(profB_lane + xl * STRIDE) = make_uint2(ob[0][j], ob[1][j]);
+                } else {
+                    *reinterpret_cast<unsigned*>(profA_lane + xl * STRIDE) = oa[0][j];
+                    *reinterpret_cast<unsigned*>(profB_lane + xl * STRIDE) = ob[0][j];
+                }
+            }
+        }
+    }
+    if constexpr (WA == 2) {
+        *reinterpret_cast<uint2*>(profA_lane + (unsigned)S * STRIDE) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2*>(profB_lane + (unsigned)S * STRIDE) = make_uint2(0u, 0u);
+    } else {
+        *reinterpret_cast<unsigned*>(profA_lane + (unsigned)S * STRIDE) = 0u;
+        *reinterpret_cast<unsigned*>(profB_lane + (unsigned)S * STRIDE) = 0u;
+    }
+}
+
 __device__ __forceinline__ unsigned prmt_generic(unsigned a, unsigned b, unsigned sel)
 {
     unsigned d;
@@ -75,42 +147,45 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
         if (p < XM) ring[p + XR] = v;
     };
 
+    // Tickets and per-pair metadata run ahead of the sweep: the atomic for the warp's second-next ticket and the metadata loads of
+    // its next ticket are issued before the chunk loop and land while it runs (three dependent global round trips otherwise).
+    struct Meta { unsigned long long pA, oyA, oxA, oyB, oxB; unsigned nA, mA, nB, mB; };
+    auto load_meta = [&](unsigned long long t) {
+        Meta q;
+        q.pA = a.first + 2 * t;
+        q.oyA = q.oxA = q.oyB = q.oxB = 0; q.nA = q.mA = q.nB = q.mB = 0;
+        if (q.pA < a.npairs) {
+            q.nA = a.lenY[q.pA]; q.mA = a.lenX[q.pA]; q.oyA = a.offY[q.pA]; q.oxA = a.offX[q.pA];
+            if (q.pA + 1 < a.npairs) { q.nB = a.lenY[q.pA + 1]; q.mB = a.lenX[q.pA + 1]; q.oyB = a.offY[q.pA + 1]; q.oxB = a.offX[q.pA + 1]; }
+        }
+        return q;
+    };
+    unsigned long long tk = 0;                       // lane 0: the ticket drawn ahead
+    if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
+    Meta nx = load_meta(__shfl_sync(kFull, tk, 0));
+    if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
+
     for (;;) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.ticket, 1ull);
-        t = __shfl_sync(kFull, t, 0);
-        const unsigned long long pA = a.first + 2 * t, pB = pA + 1;
+        const Meta cu = nx;
+        const unsigned long long pA = cu.pA, pB = pA + 1;
         if (pA >= a.npairs) break;
         const bool hasB = pB < a.npairs;
-        int nA = (int)a.lenY[pA], mA = (int)a.lenX[pA];
-        int nB = hasB ? (int)a.lenY[pB] : 0, mB = hasB ? (int)a.lenX[pB] : 0;
+        int nA = (int)cu.nA, mA = (int)cu.mA, nB = (int)cu.nB, mB = (int)cu.mB;
         const int gapsA = (nA + mA) * a.gap, gapsB = (nB + mB) * a.gap;
         const bool tallA = nA > By, tallB = nB > By;
         if (tallA) { nA = 0; mA = 0; }                     // swept as an empty pair; the host re-runs it as a single pair
         if (tallB) { nB = 0; mB = 0; }
         if (nA == 0) mA = 0;
         if (nB == 0) mB = 0;
-        const uint8_t* yA = a.letters + a.offY[pA];
-        const uint8_t* xA = a.letters + a.offX[pA];
-        const uint8_t* yB = a.letters + a.offY[hasB ? pB : pA];
-        const uint8_t* xB = a.letters + a.offX[hasB ? pB : pA];
+        const uint8_t* yA = a.letters + cu.oyA;
+        const uint8_t* xA = a.letters + cu.oxA;
+        const uint8_t* yB = a.letters + cu.oyB;
+        const uint8_t* xB = a.letters + cu.oxB;
         const int m = max(mA, mB);
         __syncwarp();
-        // ---- pair A: byte profile (shared code with the 32-bit kernels)
-        const int padA = By - nA, padB = By - nB;
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int i = lane * R - padA + r;
-            if (i >= 0 && i < nA && (unsigned)__ldg(yA + i) >= (unsigned)S) *a.err = 1;
-        }
-        build_profile<R, 1>(smA, sp_tab, S, yA, (long long)lane * R - padA, nA, lane, nullptr);
-        // ---- pair B: the same layout with doubled bytes
-#pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int i = lane * R - padB + r;
-            if (i >= 0 && i < nB && (unsigned)__ldg(yB + i) >= (unsigned)S) *a.err = 1;
-        }
-        build_profile<R, 1, SHLB>(smB, sp_tab, S, yB, (long long)lane * R - padB, nB, lane, nullptr);
+        // ---- the two byte profiles (pair B's IDP.2A words doubled); rows are aligned to the bottom of the band per pair
+        build_profiles2<R, SHLB>(smA.prof + lane * 4 * WA, smB.prof + lane * 4 * WA, sp_tab, S,
+                                 yA, lane * R - (By - nA), nA, yB, lane * R - (By - nB), nB, a.err);
         // ---- letter ring: columns -32..-1 are outside (zero row), then PD groups ahead
         auto fetch = [&](int c, unsigned& la, unsigned& lb) {
             la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;
@@ -133,6 +208,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
         for (int r = 0; r < R; r++) h[r] = 0u;
         unsigned dprev = 0u;
         const int nlc = S2::nlc(m);
+        nx = load_meta(__shfl_sync(kFull, tk, 0));
+        if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
             unsigned pf_a, pf_b;
