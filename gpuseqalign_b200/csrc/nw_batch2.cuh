@@ -31,10 +31,11 @@ struct Sched2 {
     __host__ __device__ static constexpr int nlc(int m) { return (m + LAG + 31) / 32; }
     __host__ __device__ static constexpr size_t warp_smem_bytes(int S)
     {
-        return (size_t)(S + 1) * STRIDE * 2 + (size_t)(XR + XM) * 8;
+        return (size_t)(2 * S + 1) * STRIDE + (size_t)(XR + XM) * 8;      // profile A | profile B | the zero row they share | ring
     }
 };
 
+constexpr int kBatch2MaxLetters = 31;      // rows of the CTA's s' table (static shared memory): 16 warps of S = 25 fit one SM with it
 constexpr int kBatch2MaxSprime = 127;      // 2 * s' must fit a byte, and 256 * s' must stay below 2^15
 
 // Both packed byte profiles of a warp's two pairs in ONE pass over the letters: prof[letter][lane][q] = bytes s'(y[row 4q..4q+3], letter)
@@ -43,7 +44,7 @@ constexpr int kBatch2MaxSprime = 127;      // 2 * s' must fit a byte, and 256 * 
 template <int R, int SHLB>
 __device__ __forceinline__ void build_profiles2(unsigned char* profA_lane, unsigned char* profB_lane, const unsigned* __restrict__ sp_tab, int S,
                                                 const uint8_t* __restrict__ yA, int i0A, int nA,
-                                                const uint8_t* __restrict__ yB, int i0B, int nB, int* err)
+                                                const uint8_t* __restrict__ yB, int i0B, int nB, int* err, unsigned char* zero_lane)
 {
     constexpr int WA = R / 4;
     constexpr unsigned STRIDE = 128 * WA;
@@ -100,13 +101,8 @@ __device__ __forceinline__ void build_profiles2(unsigned char* profA_lane, unsig
             }
         }
     }
-    if constexpr (WA == 2) {
-        *reinterpret_cast<uint2*>(profA_lane + (unsigned)S * STRIDE) = make_uint2(0u, 0u);
-        *reinterpret_cast<uint2*>(profB_lane + (unsigned)S * STRIDE) = make_uint2(0u, 0u);
-    } else {
-        *reinterpret_cast<unsigned*>(profA_lane + (unsigned)S * STRIDE) = 0u;
-        *reinterpret_cast<unsigned*>(profB_lane + (unsigned)S * STRIDE) = 0u;
-    }
+    if constexpr (WA == 2) *reinterpret_cast<uint2*>(zero_lane) = make_uint2(0u, 0u);
+    else *reinterpret_cast<unsigned*>(zero_lane) = 0u;
 }
 
 __device__ __forceinline__ unsigned prmt_generic(unsigned a, unsigned b, unsigned sel)
@@ -127,22 +123,23 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
     using S2 = Sched2<R>;
     constexpr int By = S2::By, WA = S2::WA, PD = S2::PD, XR = S2::XR, XM = S2::XM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned sp_tab[kSpWords];
-    stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
+    __shared__ unsigned sp_tab[(kBatch2MaxLetters + 1) * kSpPitch];
+    stage_sprime(sp_tab, a.sprime, a.S, smem_raw, (kBatch2MaxLetters + 1) * kSpPitch);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int S = a.S;
     unsigned char* base = smem_raw + (size_t)w * S2::warp_smem_bytes(S);
-    WarpSmem<R, 1> smA(base, S), smB(base + (size_t)(S + 1) * S2::STRIDE, S);      // only .prof is used (build_profile)
-    uint2* ring = reinterpret_cast<uint2*>(base + (size_t)(S + 1) * S2::STRIDE * 2);  // [XR + XM]
+    unsigned char* profA = base;                                     // [S][32 lanes][WA words]
+    unsigned char* profB = base + (size_t)S * S2::STRIDE;            // [S][32][WA]; row S of B = row 2S of A = the zero row
+    uint2* ring = reinterpret_cast<uint2*>(base + (size_t)(2 * S + 1) * S2::STRIDE);  // [XR + XM]
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
-    const unsigned laneA_s = (unsigned)__cvta_generic_to_shared(smA.prof) + lane * 4 * WA;
-    const unsigned laneB_s = (unsigned)__cvta_generic_to_shared(smB.prof) + lane * 4 * WA;
+    const unsigned laneA_s = (unsigned)__cvta_generic_to_shared(profA) + lane * 4 * WA;
+    const unsigned laneB_s = (unsigned)__cvta_generic_to_shared(profB) + lane * 4 * WA;
     const int src_lane = (lane + 31) & 31;
     const bool last = lane == 31;
 
     auto put_letters = [&](int c, unsigned la, unsigned lb) {
         const int p = c & (XR - 1);
-        const uint2 v = make_uint2(la * S2::STRIDE, lb * S2::STRIDE);
+        const uint2 v = make_uint2((la < (unsigned)S ? la : 2u * (unsigned)S) * S2::STRIDE, lb * S2::STRIDE);      // letter S = the zero row
         ring[p] = v;
         if (p < XM) ring[p + XR] = v;
     };
@@ -184,8 +181,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
         const int m = max(mA, mB);
         __syncwarp();
         // ---- the two byte profiles (pair B's IDP.2A words doubled); rows are aligned to the bottom of the band per pair
-        build_profiles2<R, SHLB>(smA.prof + lane * 4 * WA, smB.prof + lane * 4 * WA, sp_tab, S,
-                                 yA, lane * R - (By - nA), nA, yB, lane * R - (By - nB), nB, a.err);
+        build_profiles2<R, SHLB>(profA + lane * 4 * WA, profB + lane * 4 * WA, sp_tab, S,
+                                 yA, lane * R - (By - nA), nA, yB, lane * R - (By - nB), nB, a.err, profB + (size_t)S * S2::STRIDE + lane * 4 * WA);
         // ---- letter ring: columns -32..-1 are outside (zero row), then PD groups ahead
         auto fetch = [&](int c, unsigned& la, unsigned& lb) {
             la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;

@@ -115,7 +115,7 @@ constexpr int kSpWords = (kMaxLetters + 1) * kSpPitch;    // static shared memor
 // into `landing` -- any 16-byte aligned shared memory of >= S*S + 15 bytes that the caller does not use yet (every kernel passes
 // the start of its dynamic shared memory) -- and is then spread into the padded rows.  (The letters themselves are consumed 32
 // bytes per chunk and warp, at arbitrary alignment: below the granularity of a bulk copy; they stay on the LDG path.)
-__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S, unsigned char* landing)
+__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S, unsigned char* landing, int words = kSpWords)
 {
     __shared__ __align__(8) unsigned long long s_mbar;
     const unsigned bytes = ((unsigned)(S * S) + 15u) & ~15u;           // the device buffer is allocated with slack (nwb200_set_scoring)
@@ -125,7 +125,7 @@ __device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < kSpWords; i += blockDim.x) sp_tab[i] = 0u;
+    for (int i = threadIdx.x; i < words; i += blockDim.x) sp_tab[i] = 0u;        // `words` < kSpWords: a table for a smaller alphabet
     __syncthreads();
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
