@@ -32,6 +32,8 @@ if ROOT not in sys.path:
 SM_COUNT = 148
 DPX_PER_CLK_PER_SM = 64.0          # measured VIMNMX3 rate (profiles/microbench_r1.jsonl): 63.96 thread-ops/clk/SM
 MIX_CELLS_PER_CLK_PER_SM = 48.3    # measured IDP.4A + VIMNMX3 pair rate (same file): cells/clk/SM of the 2-instruction cell
+MIX16_CELLS_PER_CLK_PER_SM = 54.2  # measured IDP.4A + IDP.2A + VIMNMX3.U16x2 rate (profiles/microbench_r1z.jsonl): the packed batch kernel's
+                                   # three instructions per TWO cells
 
 
 def load_scoring():
@@ -353,13 +355,23 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
                          # (profiles/r1y_ncu_fill_cluster16_16k.txt: 35.5 MB for the 16k pair under the profiler's cold caches --
                          # header rows, middle rows, origin maps and snapshots, 59 MB in all, live in L2 otherwise;
-                         # profiles/r1u_ncu_batch_*.txt: 543 B per pair)
+                         # profiles/r1z_ncu_batch2_*.txt: 544 B per pair)
                          "traffic": (35489792 if (args.workload == "pair16k" and args.len == 16384 and with_trace) else
-                                     (546.0 * per if args.workload == "batch256" else None)),
-                         "kernel": "nw_fill_kernel" if args.workload == "pair16k" else "nw_batch_kernel", "kernel_ms": fill_ms,
+                                     (544.2 * per if args.workload == "batch256" else None)),
+                         "kernel": "nw_fill_kernel" if args.workload == "pair16k" else
+                                   ("nw_batch_kernel" if os.environ.get("NWB200_BATCH_PACKED", "1").startswith("0") else "nw_batch2_kernel"),
+                         "kernel_ms": fill_ms,
                          "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz}}
+    if args.workload == "batch256" and line["roofline"]["kernel"] == "nw_batch2_kernel":
+        # the packed kernel computes TWO cells per VIMNMX3.U16x2: against a roofline of one DPX op per two cells the same rate is half
+        # the fraction; both are reported, together with the measured rate of the kernel's own three-instruction mix
+        line["roofline"]["peak_packed16"] = 2.0 * peak
+        line["roofline"]["frac_packed16"] = achieved / (2.0 * peak)
+        line["roofline"]["peak_mix_measured"] = SM_COUNT * MIX16_CELLS_PER_CLK_PER_SM * f_ghz
+        line["roofline"]["frac_of_mix_measured"] = achieved / (SM_COUNT * MIX16_CELLS_PER_CLK_PER_SM * f_ghz)
+        line["dtype"] = "u16x2 (two pairs per 32-bit register)"
     if world == 1 and not args.no_cpu_baseline:
         try:
             if args.workload == "pair16k":

@@ -99,6 +99,9 @@ struct nwb200_ctx {
     nwb::DevBuf d_bletters, d_bmeta, d_bscores, d_bticket;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t slice_ev[48] = {};
+    cudaStream_t d2h_stream = nullptr;          // scores of a finished slice travel back while later slices are still arriving
+    cudaEvent_t slice_done_ev[48] = {};
+    nwb::PinBuf h_bscores;
     size_t batch_pairs = 0, batch_letters = 0;
     int batch_maxy = 0;
     bool batch_resident = false;

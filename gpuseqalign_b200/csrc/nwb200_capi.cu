@@ -172,6 +172,8 @@ void nwb200_destroy(nwb200_ctx* c)
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->slice_ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& e : c->slice_done_ev) if (e) cudaEventDestroy(e);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
