@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
 
     // Tickets and per-pair metadata run ahead of the sweep: the atomic for the warp's second-next ticket and the metadata loads of
     // its next ticket are issued before the chunk loop and land while it runs (three dependent global round trips otherwise).
+    // (Tried and dropped: the profile build fully unrolled over the letter groups -- fewer instructions, but ptxas then caps the
+    // kernel at 64 registers and the sweep loses 5 %.)
     struct Meta { unsigned long long pA, oyA, oxA, oyB, oxB; unsigned nA, mA, nB, mB; };
     auto load_meta = [&](unsigned long long t) {
         Meta q;
@@ -211,9 +213,9 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
             const int cp = 32 * (lc + PD) + lane;
             unsigned pf_a, pf_b;
             fetch(cp, pf_a, pf_b);                                               // checked when it lands, after the chunk
-            // The loads are volatile asm with shared-space addresses so that they stay where they are written: the letter offsets
-            // three steps and the profile words two steps ahead of their use (left to itself the compiler sinks the profile loads
-            // to one step ahead to save registers, and every step then waits for shared memory).
+            // Shared-space addresses (32-bit) for the loads of the chunk: letter offsets are requested three steps, profile words two
+            // steps ahead of their use (ptxas still sinks the profile loads towards their use to save registers; the 16 warps of an
+            // SM cover what is left of the shared-memory latency: short_sb is 6 % of the stall samples).
             const unsigned xs_s = ring_s + 8u * (unsigned)((32 * lc - lane) & (XR - 1));
             uint2 xo[32];
             unsigned wa[32][WA], wb[32][WA];
