@@ -196,6 +196,30 @@ def run_reference_arm(args):
 
 
 # --------------------------------------------------------------------------------- this engine
+def bind_to_gpu_numa_node(torch, local):
+    """One process per GPU: run (and therefore first-touch / pin host buffers) on the CPUs next to this rank's GPU, so that H2D
+    slices do not cross the socket interconnect.  Returns the cpulist used, or None when sysfs does not say."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return txt
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -222,6 +246,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -364,6 +389,8 @@ def main():
                          "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz}}
+    if numa:
+        line["config"]["cpu_affinity"] = f"rank 0 bound to the CPUs next to its GPU ({numa}); every rank does the same"
     if args.workload == "batch256" and line["roofline"]["kernel"] == "nw_batch2_kernel":
         # the packed kernel computes TWO cells per VIMNMX3.U16x2: against a roofline of one DPX op per two cells the same rate is half
         # the fraction; both are reported, together with the measured rate of the kernel's own three-instruction mix

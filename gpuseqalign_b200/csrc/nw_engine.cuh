@@ -102,6 +102,8 @@ struct nwb200_ctx {
     cudaStream_t d2h_stream = nullptr;          // scores of a finished slice travel back while later slices are still arriving
     cudaEvent_t slice_done_ev[48] = {};
     nwb::PinBuf h_bscores;
+    nwb::DevBuf d_bmoves, d_bmoff, d_bcnt;      // transcripts of a batch: move lists, their offsets, their lengths
+    nwb::PinBuf h_bmoves;
     size_t batch_pairs = 0, batch_letters = 0;
     int batch_maxy = 0;
     bool batch_resident = false;

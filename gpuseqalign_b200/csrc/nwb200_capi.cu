@@ -166,9 +166,10 @@ void nwb200_destroy(nwb200_ctx* c)
     if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
                       &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
-                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_dbg, &c->d_wave})
+                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})
         b->release();
     c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release(); c->h_export.release();
+    c->h_bscores.release(); c->h_bmoves.release();
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     for (auto& e : c->slice_ev) if (e) cudaEventDestroy(e);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

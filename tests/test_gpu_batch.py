@@ -136,3 +136,28 @@ def test_batch_packed_halves_at_their_bound(scoring, oracle):
         exp = oracle.score_batch(pool, offY, lenY, offX, lenX, subst.ravel(), -11)      # the oracle takes the flat S*S table
         assert np.array_equal(got, exp), diag
         assert got[0] == 256 * diag
+
+
+@pytest.mark.parametrize("n_pairs,max_y,max_x", [(300, 256, 256), (200, 128, 400), (64, 512, 512), (50, 40, 3000), (24, 300, 2000), (10, 700, 300)])
+def test_batch_transcripts_kernel(engine, scoring, oracle, n_pairs, max_y, max_x):
+    """Transcripts of a whole batch come from one warp per pair (nw_batch_trace_kernel: move codes of every cell in shared memory,
+    then the walk); empty sequences and pairs wider than the shared memory take the single-pair path.  Every pair vs the oracle."""
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(5000 + n_pairs)
+    letters, offY, lenY, offX, lenX = _ragged(rng, n_pairs, max_y, max_x)
+    # a few near-identical pairs (long diagonal runs) and one-sided pairs (long gap runs)
+    for p in range(0, n_pairs, 7):
+        k = int(min(lenY[p], lenX[p]))
+        letters[int(offY[p]): int(offY[p]) + k] = letters[int(offX[p]): int(offX[p]) + k]
+    l0 = engine.launches()
+    scores, edits, hashes = engine.align_batch(letters, offY, lenY, offX, lenX, want_trace=True)
+    for p in range(n_pairs):
+        y = letters[int(offY[p]): int(offY[p]) + int(lenY[p])]
+        x = letters[int(offX[p]): int(offX[p]) + int(lenX[p])]
+        if y.size == 0 or x.size == 0:
+            assert scores[p] == -11 * (y.size + x.size)
+            continue
+        exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+        assert (scores[p], edits[p], hashes[p]) == (exp.score, exp.edit, exp.trace_hash), p
+    if max_x <= 512 and max_y <= 512:
+        assert engine.launches() - l0 < 40, "transcripts must not go pair by pair"
