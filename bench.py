@@ -118,8 +118,8 @@ def cpu_reference_pair(y, x, subst, gap, samples, warmup):
     """The reference's own cpu4-mt-diagrow (+ NwTrace1_Plain) from oracle/_ref when it was prebuilt, else the
     C restatement (oracle port).  Returns (gcups, kind, cores, ms_per_sample)."""
     from oracle import pyoracle
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+    cores = int(os.environ["OMP_NUM_THREADS"])            # the threads actually used
     cells = float(y.size) * float(x.size)
     times = []
     if pyoracle.ref_available():
@@ -166,6 +166,10 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; this arm is ONE process that owns the host (the other ranks have left):
+    # give the reference's OpenMP path all the cores, as at N = 1
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from gpuseqalign_b200 import synth
     subst, gap = load_scoring()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
@@ -246,7 +250,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
+    # (only where host-to-device traffic matters: the batch workload moves 562 MB per step and rank)
+    numa = bind_to_gpu_numa_node(torch, local) if (world > 1 and args.workload == "batch256") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
