@@ -394,6 +394,17 @@ def main():
                          "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz}}
+    if args.workload == "pair16k" and fill_ms > 0:
+        # A lone pair is bound by its chain of dependent steps, not by issue slots: bands of 128 rows, a lane
+        # R = 4 rows deep, lanes two steps apart, a band following the one above at the lane pipeline + one hand-off group.
+        # Floor of a step = its R dependent VIMNMX3 (4.47 clk each, profiles/microbench_r1.jsonl).
+        R_, K_, grp = 4, 2, 8
+        nb_ = (n + 32 * R_ - 1) // (32 * R_)
+        dep_steps = m + 31 * K_ + (nb_ - 1) * (31 * K_ + grp)
+        floor_ms = dep_steps * R_ * 4.47 / (f_ghz * 1e6)
+        line["roofline"]["latency_floor"] = {"dependent_steps": dep_steps, "clk_per_step_floor": R_ * 4.47, "ms": floor_ms,
+                                             "frac": floor_ms / fill_ms,
+                                             "note": "critical path of the band wavefront at the DPX dependent-issue latency; the fill kernel's time against it"}
     if numa:
         line["config"]["cpu_affinity"] = f"rank 0 bound to the CPUs next to its GPU ({numa}); every rank does the same"
     if args.workload == "batch256" and line["roofline"]["kernel"] == "nw_batch2_kernel":
