@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
 // half-band maps of a 16k pair.  The path runs roughly along the line to the origin, so the warp copies, kHopAhead lookups ahead,
 // the 1024 map entries around the column that line predicts into shared memory (cp.async, one group per lookup): the dependent
 // load then is a shared-memory read.  A wrong guess costs the L2 round trip, never the result.
-constexpr int kHopAhead = 10, kHopWin = 1024;
+constexpr int kHopAhead = 10, kHopWin = 256;
 __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, int cut_lag, int cut_slots)      // cut_lag = 31*K, cut_slots = R+2
 {
     __shared__ __align__(16) int win[kHopAhead][kHopWin];
