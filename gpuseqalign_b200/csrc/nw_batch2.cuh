@@ -182,10 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
         const uint8_t* xB = a.letters + cu.oxB;
         const int m = max(mA, mB);
         __syncwarp();
-        // ---- the two byte profiles (pair B's IDP.2A words doubled); rows are aligned to the bottom of the band per pair
-        build_profiles2<R, SHLB>(profA + lane * 4 * WA, profB + lane * 4 * WA, sp_tab, S,
-                                 yA, lane * R - (By - nA), nA, yB, lane * R - (By - nB), nB, a.err, profB + (size_t)S * S2::STRIDE + lane * 4 * WA);
-        // ---- letter ring: columns -32..-1 are outside (zero row), then PD groups ahead
+        // ---- the first PD letter groups are requested before the profiles are built and land under the build
         auto fetch = [&](int c, unsigned& la, unsigned& lb) {
             la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;
             lb = c < mB ? (unsigned)__ldg(xB + c) : (unsigned)S;
@@ -195,12 +192,16 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
             if (lb > (unsigned)S) { lb = (unsigned)S; *a.err = 1; }
             put_letters(c, la, lb);
         };
-        put_letters(-32 + lane, (unsigned)S, (unsigned)S);      // (ZOFF for both pairs)
-        for (int g = 0; g < PD; g++) {
-            unsigned la, lb;
-            fetch(32 * g + lane, la, lb);
-            check_put(32 * g + lane, la, lb);
-        }
+        unsigned fa[PD], fb[PD];
+#pragma unroll
+        for (int g = 0; g < PD; g++) fetch(32 * g + lane, fa[g], fb[g]);
+        // ---- the two byte profiles (pair B's IDP.2A words doubled); rows are aligned to the bottom of the band per pair
+        build_profiles2<R, SHLB>(profA + lane * 4 * WA, profB + lane * 4 * WA, sp_tab, S,
+                                 yA, lane * R - (By - nA), nA, yB, lane * R - (By - nB), nB, a.err, profB + (size_t)S * S2::STRIDE + lane * 4 * WA);
+        // ---- letter ring: columns -32..-1 are outside (zero row), then the PD groups
+        put_letters(-32 + lane, (unsigned)S, (unsigned)S);
+#pragma unroll
+        for (int g = 0; g < PD; g++) check_put(32 * g + lane, fa[g], fb[g]);
         __syncwarp();
         unsigned h[R];
 #pragma unroll
