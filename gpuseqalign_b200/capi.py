@@ -85,7 +85,7 @@ EXPORTS = [
     "nwb200_batch_resident", "nwb200_fetch_batch_scores", "nwb200_last_cuda_error", "nwb200_last_error",
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
-    "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch",
+    "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
 ]
 
 _lib = None
@@ -131,6 +131,7 @@ def load_library():
     L.nwb200_sync.argtypes = [vp]
     L.nwb200_kernel_launches.argtypes = [vp]
     L.nwb200_version.restype = C.c_char_p
+    L.nwb200_batch_kernel_name.argtypes = [vp]; L.nwb200_batch_kernel_name.restype = C.c_char_p
     L.nwb200_wave_upload.argtypes = [vp, vp, i64, vp, i64, P(_Params), C.c_int, C.c_int, C.c_int]
     L.nwb200_wave_export.argtypes = [vp, vp]
     L.nwb200_wave_connect.argtypes = [vp, vp]
@@ -283,12 +284,19 @@ class Engine:
         self._check(self._L.nwb200_fetch_batch_scores(self._h, _ptr(out)))
         return out
 
-    def align_batch(self, letters, offY, lenY, offX, lenX, want_trace: bool = False):
+    def align_batch(self, letters, offY, lenY, offX, lenX, want_trace: bool = False, out: Optional[np.ndarray] = None):
+        """Scores of a batch of pairs from host buffers (H2D, kernels and D2H overlapped slice by slice); ``out``: a caller-owned
+        int32 array for the scores (pinned memory saves the staging copy)."""
         letters = np.ascontiguousarray(letters, dtype=np.uint8)
         offY = np.ascontiguousarray(offY, dtype=np.uint64); offX = np.ascontiguousarray(offX, dtype=np.uint64)
         lenY = np.ascontiguousarray(lenY, dtype=np.uint32); lenX = np.ascontiguousarray(lenX, dtype=np.uint32)
         n = lenY.size
-        scores = np.empty(n, dtype=np.int32)
+        if out is not None:
+            if out.dtype != np.int32 or out.size != n or not out.flags.c_contiguous:
+                raise NwB200Error(NwStat.errorInvalidValue, "out must be a contiguous int32 array with one entry per pair")
+            scores = out
+        else:
+            scores = np.empty(n, dtype=np.int32)
         if not want_trace:
             self._check(self._L.nwb200_align_batch(self._h, _ptr(letters), letters.size, _ptr(offY), _ptr(lenY), _ptr(offX), _ptr(lenX), n,
                                                    _ptr(scores), None, None, None, None))
@@ -358,3 +366,6 @@ class Engine:
 
     def launches(self) -> int:
         return int(self._L.nwb200_kernel_launches(self._h))
+
+    def batch_kernel_name(self) -> str:
+        return (self._L.nwb200_batch_kernel_name(self._h) or b"").decode()

@@ -27,6 +27,8 @@ struct BatchArgs {
 };
 
 constexpr int kBatchTooTall = (int)0x80000000;
+constexpr unsigned kPastEnd = 0x100u;      // "no letter here" while a byte letter is in flight: distinct from every byte, so that a real
+                                           // letter equal to S (the internal zero-row code) is still reported as outside the alphabet
 
 template <int R, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
@@ -66,8 +68,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         for (int c = -32 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
         for (int g = 0; g < PD; g++) {
             const int c = 32 * g + lane;
-            unsigned v = c < m ? (unsigned)__ldg(x + c) : (unsigned)a.S;
-            if (v > (unsigned)a.S) { v = (unsigned)a.S; *a.err = 1; }
+            unsigned v = c < m ? (unsigned)__ldg(x + c) : kPastEnd;
+            if (v >= (unsigned)a.S) { if (v != kPastEnd) *a.err = 1; v = (unsigned)a.S; }      // a real letter must be < S
             sm.put_letter(c, v * SC::LSTRIDE);
         }
         __syncwarp();
@@ -78,11 +80,11 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         const int nlc = SC::nlc(m);
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
-            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : (unsigned)a.S;      // checked and scaled when it lands
+            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : kPastEnd;           // checked and scaled when it lands
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             sweep_chunk<R, K, 0, false>(st, lane, io, nullptr);
             __syncwarp();
-            if (pf_x > (unsigned)a.S) { pf_x = (unsigned)a.S; *a.err = 1; }
+            if (pf_x >= (unsigned)a.S) { if (pf_x != kPastEnd) *a.err = 1; pf_x = (unsigned)a.S; }
             sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
         }

@@ -48,20 +48,21 @@ __device__ __forceinline__ void build_profiles2(unsigned char* profA_lane, unsig
 {
     constexpr int WA = R / 4;
     constexpr unsigned STRIDE = 128 * WA;
+    // letter S is the INTERNAL code of a padding row (the zero row of the s' table); a real letter must be < S
     unsigned ya[R], yb[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int ia = i0A + r, ib = i0B + r;
-        ya[r] = (ia >= 0 && ia < nA) ? (unsigned)__ldg(yA + ia) : (unsigned)S;
-        yb[r] = (ib >= 0 && ib < nB) ? (unsigned)__ldg(yB + ib) : (unsigned)S;
+        ya[r] = (ia >= 0 && ia < nA) ? (unsigned)__ldg(yA + ia) : kPastEnd;
+        yb[r] = (ib >= 0 && ib < nB) ? (unsigned)__ldg(yB + ib) : kPastEnd;
     }
     const unsigned* rowA[R];
     const unsigned* rowB[R];
     bool bad = false;
 #pragma unroll
     for (int r = 0; r < R; r++) {
-        if (ya[r] > (unsigned)S) { ya[r] = (unsigned)S; bad = true; }
-        if (yb[r] > (unsigned)S) { yb[r] = (unsigned)S; bad = true; }
+        if (ya[r] >= (unsigned)S) { bad |= ya[r] != kPastEnd; ya[r] = (unsigned)S; }
+        if (yb[r] >= (unsigned)S) { bad |= yb[r] != kPastEnd; yb[r] = (unsigned)S; }
         rowA[r] = sp_tab + ya[r] * kSpPitch;
         rowB[r] = sp_tab + yb[r] * kSpPitch;
     }
@@ -184,12 +185,12 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch2_kernel(const BatchArgs a
         __syncwarp();
         // ---- the first PD letter groups are requested before the profiles are built and land under the build
         auto fetch = [&](int c, unsigned& la, unsigned& lb) {
-            la = c < mA ? (unsigned)__ldg(xA + c) : (unsigned)S;
-            lb = c < mB ? (unsigned)__ldg(xB + c) : (unsigned)S;
+            la = c < mA ? (unsigned)__ldg(xA + c) : kPastEnd;
+            lb = c < mB ? (unsigned)__ldg(xB + c) : kPastEnd;
         };
-        auto check_put = [&](int c, unsigned la, unsigned lb) {
-            if (la > (unsigned)S) { la = (unsigned)S; *a.err = 1; }
-            if (lb > (unsigned)S) { lb = (unsigned)S; *a.err = 1; }
+        auto check_put = [&](int c, unsigned la, unsigned lb) {        // a real letter must be < S; S itself is the internal zero-row code
+            if (la >= (unsigned)S) { if (la != kPastEnd) *a.err = 1; la = (unsigned)S; }
+            if (lb >= (unsigned)S) { if (lb != kPastEnd) *a.err = 1; lb = (unsigned)S; }
             put_letters(c, la, lb);
         };
         unsigned fa[PD], fb[PD];

@@ -126,6 +126,7 @@ struct nwb200_ctx {
     nwb200_timing timing = {};
     unsigned epoch = 0;
     int launches = 0;
+    const char* batch_kernel = "";
     cudaError_t last_cuda = cudaSuccess;
     std::string last_error;
 };

@@ -68,14 +68,17 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
     // other SMs are idle (measured: fill warps that share their SM sub-partition with a map warp ran 1.5x slower) -- by asking
     // for more than half of an SM's shared memory.
     if (grid <= c->sm_count && smem < 120 * 1024) smem = 120 * 1024;
-    static size_t attr_set = 0;      // per kernel instance (function-local static of the template)
+    // cudaFuncSetAttribute applies to the CURRENT device: cached per kernel instance (function-local static of the template) AND device
+    static size_t attr_set_dev[64] = {};
+    static bool nonportable_dev[64] = {};
+    size_t& attr_set = attr_set_dev[c->device & 63];
+    bool& nonportable = nonportable_dev[c->device & 63];
     if (smem > 48 * 1024 && smem > attr_set) {
         cudaError_t e = cudaFuncSetAttribute(nw_fill_kernel<R, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(fill)", e);
         attr_set = smem;
     }
     cudaError_t e = cudaSuccess;
-    static bool nonportable = false;
     if (cluster > 8 && !nonportable) {
         e = cudaFuncSetAttribute(nw_fill_kernel<R, K, W>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(non-portable cluster)", e);
@@ -457,5 +460,6 @@ int nwb200_sync(nwb200_ctx* c)
     return NWB200_SUCCESS;
 }
 int nwb200_kernel_launches(const nwb200_ctx* c) { return c ? c->launches : 0; }
+const char* nwb200_batch_kernel_name(const nwb200_ctx* c) { return c ? c->batch_kernel : ""; }
 
 }  // extern "C"

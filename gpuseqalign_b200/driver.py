@@ -52,9 +52,11 @@ def run(subst_path: str, seq_path: str, pair_path: Optional[str], out_path: Opti
     seqs = formats.read_fasta(seq_path, subst)
     if pair_path:
         pairs = formats.read_pairs(pair_path, seqs)
-    else:           # no pair file: every sequence against the first one (cmd_parser.cpp:467-499)
+    else:           # no pair file: every OTHER sequence (rows, Y) against the first one (columns, X) -- cmd_parser.cpp:466-487
+        if len(seqs.ids) < 2:
+            raise formats.FormatError("at least two sequences are needed when no pair file is given")
         first = seqs.ids[0]
-        pairs = [formats.SeqPair(first, sid, formats.SeqRange(), formats.SeqRange()) for sid in seqs.ids]
+        pairs = [formats.SeqPair(sid, first, formats.SeqRange(), formats.SeqRange()) for sid in seqs.ids[1:]]
     own = engine is None
     eng = engine or Engine(device)
     try:

@@ -97,7 +97,9 @@ typedef struct nwb200_timing {
 NWB200_API int  nwb200_create(nwb200_ctx** out, int device);
 NWB200_API void nwb200_destroy(nwb200_ctx* ctx);
 
-/* Replaces initNwInput's subst upload + gapoCost (benchmark.cpp:185-220). */
+/* Replaces initNwInput's subst upload + gapoCost (benchmark.cpp:185-220).  Restrictions the reference does not
+ * have (it takes any int): substsz <= 63 and subst[i] - 2*gap <= 255 for every entry (the kernels keep
+ * s' = max(subst - 2*gap, 0) as a byte profile); violations return NWB200_ERR_INVALID_VALUE. */
 NWB200_API int  nwb200_set_scoring(nwb200_ctx* ctx, const int32_t* subst, int substsz, int gap);
 
 /* Replaces NwAlign_Gpu9_Mlsp_DiagDiagDiag (nwalign_gpu9_mlsp_diagdiagdiag.cu:368-722):
@@ -143,14 +145,17 @@ NWB200_API int  nwb200_score_hash(nwb200_ctx* ctx, uint32_t* score_hash);
 
 /* Batch of independent pairs (BASELINE config 3): byte letters in one pool, per-pair
  * offsets/lengths.  scores[n_pairs] always; if edits != NULL each pair's transcript is written
- * at edits + edit_off[p] (edit_off[n_pairs] entries in, lengths in edit_len[p] out) and its
- * trace hash into trace_hashes[p]. */
+ * at edits + edit_off[p] (edit_off has n_pairs + 1 entries: pair p owns the bytes [edit_off[p], edit_off[p+1]);
+ * lengths in edit_len[p] out) and its trace hash into trace_hashes[p].  Letters must be < substsz
+ * (NWB200_ERR_INVALID_VALUE otherwise).  Pairs of any height are accepted (those taller than 512 rows are
+ * re-run through the single-pair kernels). */
 NWB200_API int  nwb200_align_batch(nwb200_ctx* ctx, const uint8_t* letters, size_t n_letters,
                                    const uint64_t* offY, const uint32_t* lenY,
                                    const uint64_t* offX, const uint32_t* lenX, size_t n_pairs,
                                    int32_t* scores, char* edits /* nullable */, const uint64_t* edit_off,
                                    uint32_t* edit_len, uint32_t* trace_hashes);
-/* Split form: upload once, run on the stream, fetch. */
+/* Split form: upload once, run on the stream, fetch.  Pairs with more than 512 rows are rejected here
+ * (NWB200_ERR_INVALID_VALUE): the split form has no single-pair fix-up pass. */
 NWB200_API int  nwb200_upload_batch(nwb200_ctx* ctx, const uint8_t* letters, size_t n_letters,
                                     const uint64_t* offY, const uint32_t* lenY,
                                     const uint64_t* offX, const uint32_t* lenX, size_t n_pairs);
@@ -186,6 +191,7 @@ NWB200_API int         nwb200_get_timing(const nwb200_ctx* ctx, nwb200_timing* o
 NWB200_API void*       nwb200_stream(const nwb200_ctx* ctx);                 /* cudaStream_t */
 NWB200_API int         nwb200_sync(nwb200_ctx* ctx);
 NWB200_API int         nwb200_kernel_launches(const nwb200_ctx* ctx);        /* kernels launched so far */
+NWB200_API const char* nwb200_batch_kernel_name(const nwb200_ctx* ctx);      /* kernel the last batch launch used ("" before one) */
 NWB200_API const char* nwb200_version(void);
 
 #ifdef __cplusplus

@@ -193,6 +193,10 @@ def ref():
         R.nwref_trace_from_headers.argtypes = [_i32p, C.c_int, _i32p, C.c_int, _i32p, C.c_int, C.c_int, _i32p, _i32p,
                                                C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_ulonglong, C.POINTER(_RefResult)]
         R.nwref_has_gpu9.restype = C.c_int
+        if hasattr(R, "nwref_batch_cpu"):
+            R.nwref_batch_cpu.restype = C.c_int
+            R.nwref_batch_cpu.argtypes = [C.c_int, _u8p, _u64p, _u32p, _u64p, _u32p, C.c_ulonglong, _i32p, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, _i32p, C.POINTER(C.c_double)]
         _ref = R
     return _ref
 
@@ -246,3 +250,20 @@ def ref_trace_from_headers(y, x, subst, gap, hrow, hcol, By, Bx, want_hash=False
         raise RuntimeError(f"reference NwTrace2_Sparse failed: NwStat={out.stat} step={out.step}")
     return RefRun(score=out.align_cost, score_hash=out.score_hash if want_hash else None, trace_hash=out.trace_hash,
                   edit=buf.raw[: out.edit_len].decode("ascii"), laps_ms={}, tiles=())
+
+
+def ref_batch_cpu(alg: str, letters, offY, lenY, offX, lenX, subst: np.ndarray, gap: int, *, threads: int = 1, blocksz: int = 256):
+    """The reference's own cpu4 / cpu1 align called once per pair (benchmark.cpp:406 semantics), the pairs dealt to `threads`
+    OpenMP threads by the shim.  Returns (scores, wall_ms)."""
+    R = ref()
+    n = len(lenY)
+    scores = np.zeros(n, dtype=np.int32)
+    ms = C.c_double(0.0)
+    substsz = int(round(len(subst) ** 0.5))
+    rc = R.nwref_batch_cpu({"cpu1": 1, "cpu4": 4}[alg], np.ascontiguousarray(letters, dtype=np.uint8),
+                           np.ascontiguousarray(offY, dtype=np.uint64), np.ascontiguousarray(lenY, dtype=np.uint32),
+                           np.ascontiguousarray(offX, dtype=np.uint64), np.ascontiguousarray(lenX, dtype=np.uint32), n,
+                           np.ascontiguousarray(subst, dtype=np.int32), substsz, gap, blocksz, threads, scores, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference {alg} batch failed rc={rc}")
+    return scores, float(ms.value)

@@ -179,6 +179,45 @@ int nwref_trace_from_headers(const int* seqY, int adjrows, const int* seqX, int 
     }
 }
 
+// cfg3 on the host, the way benchmark.cpp:406-517 would run it: the reference's own cpu4 (or cpu1) align called ONCE PER
+// PAIR on a freshly filled NwAlgInput (benchmark.cpp:411-426, reset after every pair :436-439).  A 256 x 256 pair is a single
+// cpu4 tile (blocksz 256), so the reference has no parallelism inside a pair; to give it every host core
+// the PAIRS are dealt to `threads` OpenMP threads here (our loop, the reference's functions; its inner `omp parallel` then runs
+// with one thread because nested parallelism is off by default).  threads <= 1: the strictly serial loop of benchmark.cpp.
+// Returns 0 and the scores; *ms_total = wall time of the loop.
+int nwref_batch_cpu(int alg, const unsigned char* letters, const unsigned long long* offY, const unsigned* lenY,
+                    const unsigned long long* offX, const unsigned* lenX, unsigned long long n_pairs,
+                    const int* subst, int substsz, int gap, int blocksz, int threads, int* scores, double* ms_total)
+{
+    if (alg != 1 && alg != 4) return 1;
+    int bad = 0;
+    Stopwatch sw {};
+    sw.start();
+    #pragma omp parallel for schedule(dynamic, 8) num_threads(threads > 1 ? threads : 1) reduction(| : bad)
+    for (long long p = 0; p < (long long)n_pairs; p++) {
+        try {
+            NwAlgInput nw {};
+            NwAlgResult res {};
+            res.cudaStat = cudaSuccess;
+            std::vector<int> sy((size_t)lenY[p] + 1, 0), sx((size_t)lenX[p] + 1, 0);
+            for (unsigned i = 0; i < lenY[p]; i++) sy[i + 1] = letters[offY[p] + i];
+            for (unsigned j = 0; j < lenX[p]; j++) sx[j + 1] = letters[offX[p] + j];
+            nwref_fill_input(nw, sy.data(), (int)sy.size(), sx.data(), (int)sx.size(), subst, substsz, gap);
+            Dict<std::string, NwAlgParam> pd;
+            if (alg == 4) pd.insert("blocksz", NwAlgParam({blocksz > 0 ? blocksz : 256}));
+            NwAlgParams pr(pd);
+            NwStat st = (alg == 4) ? NwAlign_Cpu4_Mt_DiagRow(pr, nw, res) : NwAlign_Cpu1_St_Row(pr, nw, res);
+            if (st != NwStat::success) bad |= 1;
+            scores[p] = res.align_cost;
+        } catch (...) {
+            bad |= 1;
+        }
+    }
+    sw.lap("batch");
+    if (ms_total) *ms_total = sw.get_or_default("batch");
+    return bad;
+}
+
 int nwref_has_gpu9(void)
 {
 #ifdef NWREF_WITH_GPU

@@ -2,7 +2,7 @@
 // "next lever"): ORDER 0 = step by step, the R rows of a step chained through their upper neighbour (what nw_sweep.cuh does);
 // ORDER 1 = in-lane wavefront, row r one step behind row r-1, so the R cells issued together are independent.
 // Same arithmetic (IDP.4A + VIMNMX3 per cell), same results; one warp per SM, clock64 around 256 chunks of 32 steps.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o lane_order_microbench lane_order_microbench.cu
+// Build (on the GPU box): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o /tmp/lane_order_microbench tools/lane_order_microbench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 

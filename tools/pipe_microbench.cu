@@ -6,8 +6,9 @@
 // mixes the kernels actually issue.  The numbers are the "R" of the integer-issue
 // roofline in DESIGN.md (SURVEY.md 8d asks for R to be measured, not assumed).
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o pipe_microbench pipe_microbench.cu
-// Run:   ./pipe_microbench            (prints one JSON object per line)
+// Build (on the GPU box; -cudart shared keeps the static runtime out of the binary):
+//        nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -cudart shared -o /tmp/pipe_microbench tools/pipe_microbench.cu
+// Run:   /tmp/pipe_microbench          (prints one JSON object per line)
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
