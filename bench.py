@@ -746,7 +746,8 @@ def main():
                          "frac": achieved / peak, "kernel": res["kernel"], "kernel_ms": kernel_ms,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of this kernel at N = 1, from the ncu --set full capture named
                          # beside it (profiles/traffic.json is rewritten with every capture; null when no capture of the current kernel exists)
-                         "traffic": traffic.get("bytes_per_launch") if cx.world == 1 else None, "traffic_source": traffic.get("source"),
+                         "traffic": (traffic.get("bytes_per_launch") or (traffic.get("bytes_per_pair", 0) * res["config"].get("pairs_per_gpu", 0)) or None),
+                         "traffic_source": traffic.get("source"),
                          "peak_source": f"{SM_COUNT} SMs x {DPX_PER_CLK_PER_SM:.0f} VIMNMX3/clk/SM (measured, profiles/microbench_r1.jsonl) x {f_ghz:.3f} GHz",
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz,
                          "peak_issue_slots": SM_COUNT * ISSUE_PER_CLK_PER_SM * f_ghz,

@@ -6,27 +6,12 @@
 // fill / drain of the systolic array costs 31 of m+31 steps), nothing touches HBM but the letters (read
 // once) and the 4-byte score.  Warps take pairs from an atomic ticket, so ragged batches balance themselves.
 #pragma once
+#include "nw_engine.cuh"
 #include "nw_sweep.cuh"
 
 namespace nwb {
 
-struct BatchArgs {
-    const uint8_t* letters;              // one byte pool
-    const unsigned long long* offY;      // per pair: offset / length of the row sequence ...
-    const unsigned* lenY;
-    const unsigned long long* offX;      // ... and of the column sequence
-    const unsigned* lenX;
-    unsigned long long first;            // this launch aligns pairs [first, npairs)
-    unsigned long long npairs;
-    const uint8_t* sprime;
-    int S;
-    int gap;
-    int* scores;                         // H[lenY][lenX] per pair; kBatchTooTall if lenY > 32*R (the host re-runs those as single pairs)
-    unsigned long long* ticket;          // zero at launch
-    int* err;                            // set to 1 when a letter outside the alphabet is met (the pair's score is then meaningless)
-};
 
-constexpr int kBatchTooTall = (int)0x80000000;
 constexpr unsigned kPastEnd = 0x100u;      // "no letter here" while a byte letter is in flight: distinct from every byte, so that a real
                                            // letter equal to S (the internal zero-row code) is still reported as outside the alphabet
 
@@ -99,22 +84,6 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
 // sweep_chunk: the reference's choice, nwtrace1_plain.cpp:29-100), then the walk from (n, m) back to (0, 0) over those codes --
 // what nw_walk_kernel does for one band of a long pair, here for a whole short pair.  Emits the move list in backward path order
 // (codes 0 '=', 1 'X', 2 'I', 3 'D'); run-length encoding + hash are O(path) byte work done by the host.
-struct BatchTraceArgs {
-    const uint8_t* letters;
-    const unsigned long long* offY;
-    const unsigned* lenY;
-    const unsigned long long* offX;
-    const unsigned* lenX;
-    unsigned long long first, npairs;    // this launch walks pairs [first, npairs)
-    const uint8_t* sprime;
-    int S;
-    int negg;                            // -gap
-    const unsigned long long* moff;      // [npairs - first]: start of pair (first + q)'s move list in `moves` (lenY + lenX bytes each)
-    unsigned char* moves;
-    int* cnt;                            // [npairs - first]: moves emitted; -1 = not handled here (empty sequence, taller than one band, or
-                                         // more columns than the CTA's shared memory holds codes for): the host takes the single-pair path
-    int chunks_cap;                      // 32-column chunks of move codes that fit behind the warp's sweep buffers
-};
 
 template <int R>
 __global__ void __launch_bounds__(32) nw_batch_trace_kernel(const BatchTraceArgs a)

@@ -71,7 +71,7 @@ __device__ __forceinline__ void st_tagged(unsigned long long* p, int v, unsigned
 }
 // Set when a wait for a tagged element gave up (a producer that never publishes must not hang the GPU): the host
 // reports errorInvalidResult.  ~2^21 polls of >= 20 ns + an L2 round trip each are several seconds.
-__device__ int g_wait_timeout = 0;
+static __device__ int g_wait_timeout = 0;      // one copy per translation unit (no relocatable device code): the batch kernels report through BatchArgs::err instead
 constexpr unsigned kMaxPolls = 1u << 22;
 // Polls do NOT sleep: __nanosleep(20) between two polls made single warps oversleep by 1-3 ms every few launches on B200 (one
 // straggling map unit then held the whole fill launch: 1.2 ms -> 4.5 ms, profiles/r1q_*); a poll is an L2 round trip anyway.

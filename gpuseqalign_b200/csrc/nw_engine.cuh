@@ -130,3 +130,62 @@ struct nwb200_ctx {
     cudaError_t last_cuda = cudaSuccess;
     std::string last_error;
 };
+
+// ---- host helpers shared by the translation units of libnwb200.so
+namespace nwb {
+
+inline int fail(nwb200_ctx* c, int stat, const char* msg, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        c->last_error = msg;
+        if (e != cudaSuccess) { c->last_cuda = e; c->last_error += std::string(": ") + cudaGetErrorString(e); }
+    }
+    return stat;
+}
+
+#define CU(c, call, stat, msg) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return nwb::fail((c), (stat), (msg), e__); } while (0)
+
+inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// What one launch of a batch kernel works on (nw_batch.cuh / nw_batch2.cuh; launched from nw_batch_launch.cu).
+struct BatchArgs {
+    const uint8_t* letters;              // byte letters of all sequences
+    const unsigned long long* offY;      // per pair: offset of the row sequence
+    const unsigned* lenY;
+    const unsigned long long* offX;
+    const unsigned* lenX;
+    unsigned long long first;            // this launch aligns pairs [first, npairs)
+    unsigned long long npairs;
+    const uint8_t* sprime;
+    int S;
+    int gap;
+    int* scores;                         // H[lenY][lenX] per pair; kBatchTooTall if lenY > 32*R (the host re-runs those as single pairs)
+    unsigned long long* ticket;          // zero at launch
+    int* err;                            // set to 1 when a letter outside the alphabet is met (the pair's score is then meaningless), 2 when the
+                                         // s' table did not arrive
+};
+constexpr int kBatchTooTall = (int)0x80000000;
+
+struct BatchTraceArgs {
+    const uint8_t* letters;
+    const unsigned long long* offY;
+    const unsigned* lenY;
+    const unsigned long long* offX;
+    const unsigned* lenX;
+    unsigned long long first, npairs;    // this launch walks pairs [first, npairs)
+    const uint8_t* sprime;
+    int S;
+    int negg;                            // -gap
+    const unsigned long long* moff;      // [npairs - first]: start of pair (first + q)'s move list in `moves` (lenY + lenX bytes each)
+    unsigned char* moves;
+    int* cnt;                            // [npairs - first]: moves emitted; -1 = not handled here (empty sequence, taller than one band, or
+                                         // more columns than the CTA's shared memory holds codes for): the host takes the single-pair path
+    int chunks_cap;                      // 32-column chunks of move codes that fit behind the warp's sweep buffers
+};
+
+// nw_batch_launch.cu: picks the kernel instance for the resident batch (c->batch_maxy, c->S, c->max_sprime) and launches it on c->stream
+int launch_batch(nwb200_ctx* c, const BatchArgs& a);
+int launch_batch_trace(nwb200_ctx* c, const BatchTraceArgs& a, int need_chunks);
+
+}  // namespace nwb
+

@@ -115,7 +115,9 @@ constexpr int kSpWords = (kMaxLetters + 1) * kSpPitch;    // static shared memor
 // into `landing` -- any 16-byte aligned shared memory of >= S*S + 15 bytes that the caller does not use yet (every kernel passes
 // the start of its dynamic shared memory) -- and is then spread into the padded rows.  (The letters themselves are consumed 32
 // bytes per chunk and warp, at arbitrary alignment: below the granularity of a bulk copy; they stay on the LDG path.)
-__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S, unsigned char* landing, int words = kSpWords)
+// `pitch` (words per row of sp_tab) defaults to kSpPitch; the packed batch kernel asks for 16-byte aligned rows.
+__device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __restrict__ sprime, int S, unsigned char* landing, int words = kSpWords,
+                                             int pitch = kSpPitch)
 {
     __shared__ __align__(8) unsigned long long s_mbar;
     const unsigned bytes = ((unsigned)(S * S) + 15u) & ~15u;           // the device buffer is allocated with slack (nwb200_set_scoring)
@@ -139,7 +141,7 @@ __device__ __forceinline__ void stage_sprime(unsigned* sp_tab, const uint8_t* __
         if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
     }
     unsigned char* t = reinterpret_cast<unsigned char*>(sp_tab);
-    for (int i = threadIdx.x; i < S * S; i += blockDim.x) t[(i / S) * (kSpPitch * 4) + (i % S)] = landing[i];
+    for (int i = threadIdx.x; i < S * S; i += blockDim.x) t[(i / S) * (pitch * 4) + (i % S)] = landing[i];
     __syncthreads();
 }
 

@@ -7,8 +7,6 @@
 #include "nw_engine.cuh"
 #include "nw_fill.cuh"
 #include "nw_trace.cuh"
-#include "nw_batch.cuh"
-#include "nw_batch2.cuh"
 #include "nw_scan.cuh"
 
 using namespace nwb;
@@ -16,19 +14,6 @@ using namespace nwb;
 #define NWB_VERSION "nwb200 0.1 (sm_100a)"
 
 namespace {
-
-int fail(nwb200_ctx* c, int stat, const char* msg, cudaError_t e = cudaSuccess)
-{
-    if (c) {
-        c->last_error = msg;
-        if (e != cudaSuccess) { c->last_cuda = e; c->last_error += std::string(": ") + cudaGetErrorString(e); }
-    }
-    return stat;
-}
-
-#define CU(c, call, stat, msg) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return fail((c), (stat), (msg), e__); } while (0)
-
-float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0.f; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // ---------------------------------------------------------------------------------------------
 // geometry: the analogue of nwalign_gpu9_mlsp_diagdiagdiag.cu:384-431

@@ -33,6 +33,8 @@ enum Op {
     OP_MIX_MAX3_LDS,       // 4x (imad+max3) + 1 lds32
     OP_DP2A,               // IDP.2A.LO.U16.U8
     OP_MIX_PACKED2,        // two pairs per register: d = dp4a(wA, sel, diag) ; d = dp2a(wB, sel2, d) ; c = vimax3_u16x2(d, up, left)
+    OP_MIX_MERGED2,        // round 2: m = prmt(wA, wB) per TWO rows ; d = dp2a_lo/hi(0x80000001, m, diag) ; c = vimax3_u16x2(d, up, left)
+    OP_MIX_DP2A_MAX3_16,   // the same without the permute (the ceiling if the two profile words came pre-merged)
     OP_COUNT
 };
 
@@ -43,7 +45,8 @@ static const char* op_names[OP_COUNT] = {
     "mix16: PRMT+VIADDMNMX16+VIMNMX16 (per 2 cells)", "mix16: VIADDMNMX16+VIMNMX16 (per 2 cells)",
     "SHFL.UP", "LDS.32", "LDS.64", "LDS.128",
     "mix: 4x(IMAD+VIMNMX3)+SHFL (per 4 cells)", "mix: 4x(IMAD+VIMNMX3)+LDS32 (per 4 cells)",
-    "IDP.2A", "mix16: IDP4A+IDP2A+VIMNMX3.U16x2 (per 2 cells)"};
+    "IDP.2A", "mix16: IDP4A+IDP2A+VIMNMX3.U16x2 (per 2 cells)",
+    "mix16: 0.5 PRMT+IDP2A+VIMNMX3.U16x2 (per 2 cells)", "mix16: IDP2A+VIMNMX3.U16x2 (per 2 cells)"};
 
 // "units" per inner-loop body per accumulator (what the reported rate counts).
 template <int OP>
@@ -63,6 +66,21 @@ __device__ __forceinline__ void body(int (&a)[ILP], int (&b)[ILP], int p, int q,
         else if (OP == OP_MIX_PACKED2) {
             unsigned d = __dp4a((unsigned)p, (unsigned)sel, (unsigned)b[k]);
             d = __dp2a_lo((unsigned)q, (unsigned)sel, d);
+            unsigned c = __vimax3_u16x2(d, (unsigned)a[k], (unsigned)b[k]);
+            b[k] = a[k]; a[k] = c;
+        }
+        else if (OP == OP_MIX_MERGED2) {
+            if ((k & 1) == 0) {
+                const unsigned m = __byte_perm((unsigned)p + (unsigned)b[k], (unsigned)q, (unsigned)sel);
+                unsigned d0 = __dp2a_lo(0x80000001u, m, (unsigned)b[k]);
+                unsigned d1 = __dp2a_hi(0x80000001u, m, (unsigned)b[k + 1]);
+                unsigned c0 = __vimax3_u16x2(d0, (unsigned)a[k], (unsigned)b[k]);
+                unsigned c1 = __vimax3_u16x2(d1, (unsigned)a[k + 1], (unsigned)b[k + 1]);
+                b[k] = a[k]; a[k] = c0; b[k + 1] = a[k + 1]; a[k + 1] = c1;
+            }
+        }
+        else if (OP == OP_MIX_DP2A_MAX3_16) {
+            unsigned d = __dp2a_lo(0x80000001u, (unsigned)p, (unsigned)b[k]);
             unsigned c = __vimax3_u16x2(d, (unsigned)a[k], (unsigned)b[k]);
             b[k] = a[k]; a[k] = c;
         }
@@ -223,6 +241,8 @@ int main() {
         run_tp<OP_MIX_MAX3_LDS>(d_out, d_cyc, sms, threads, 8, "cells");
         run_tp<OP_DP2A>(d_out, d_cyc, sms, threads, ILP, "ops");
         run_tp<OP_MIX_PACKED2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
+        run_tp<OP_MIX_MERGED2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
+        run_tp<OP_MIX_DP2A_MAX3_16>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
     }
     run_lat<OP_VIMNMX3>(d_out, d_cyc);
     run_lat<OP_VIADDMNMX>(d_out, d_cyc);
