@@ -575,7 +575,7 @@ def wl_wave(cx: Ctx, steps, warmup, main):
                 "e2e": {"value": cells * e2e_steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * n), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_s / e2e_steps * 1e3},
                 "parity": parity, "dtype": "int32"}
-    block = args.wave_block
+    block = args.wave_block if args.wave_block > 0 else max(2048, ((n + cx.world - 1) // cx.world + 31) // 32 * 32)
     wave_setup(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block)
     sampler = ClockSampler(cx.local) if main else None
     if sampler:
@@ -701,7 +701,8 @@ def main():
     ap.add_argument("--len", type=int, default=16384, help="pair16k: sequence length")
     ap.add_argument("--pairs", type=int, default=1 << 20, help="batch256: pairs in the whole job")
     ap.add_argument("--wave-len", type=int, default=200000, help="wave200k: sequence length")
-    ap.add_argument("--wave-block", type=int, default=2048, help="wave200k, N > 1: columns per block")
+    ap.add_argument("--wave-block", type=int, default=0, help="wave200k, N > 1: columns per block (0: one block per rank, the measured optimum -- "
+                                                                "profiles/r2k_wave_probe_blocks.jsonl; every block boundary re-staggers the band wavefront)")
     ap.add_argument("--scan-rows", type=int, default=2048)
     ap.add_argument("--scan-cols", type=int, default=4194304)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -6,6 +6,8 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <utility>
 #include <cuda_runtime.h>
 #include "../../include/nwb200.h"
 
@@ -109,6 +111,7 @@ struct nwb200_ctx {
     bool batch_resident = false;
     nwb::PinBuf h_batch;
     // cross-GPU column-block wavefront
+    nwb::DevBuf d_order;             // ticket -> (block round, band) in wavefront order
     nwb::DevBuf d_wave;              // [flags (nq+1)*nb | err, pad | recv (nq+1)*recv_stride] -- ONE allocation, exported over CUDA IPC
     void* wave_peer_base = nullptr;  // the right neighbour's d_wave mapped into this process (nullptr: loopback)
     int wave_rank = 0, wave_world = 1, wave_wc = 0, wave_nq = 0, wave_nblocks = 0;

@@ -51,6 +51,9 @@ struct FillArgs {
     unsigned tag;            // epoch tag of this run's header rows (never 0; local to this GPU)
     unsigned xtag;           // epoch tag of the cross-GPU border flags (the same on every rank)
     int* ticket;             // (block, band) ticket counter
+    const int2* order;       // nullable: ticket t -> (q, b).  Column blocks: units in the order of the wavefront (start time g*U + b*L), so that
+                             // the window of tickets in flight follows the diagonal of active units instead of holding whole blocks whose
+                             // lower bands cannot start yet (block-major tickets, block 2 048: 1 unit in 8 of the window was runnable)
     int nb;                  // number of bands
     int pad;                 // padding rows above row 1 in band 0 (nb*By - n)
     unsigned long long* dbg; // developer aid: [nb][4] globaltimer stamps (start, prologue done, end) + poll count; nullable
@@ -216,7 +219,9 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;      // profile offset of the all-zero row
     const int nblocks = (a.m + a.wc - 1) / a.wc;             // column blocks of the whole matrix
     constexpr int L4 = SC::L4, HB0 = SC::LAG - SC::L4;     // HB0: ring position of quad 0 of chunk 0
-    const int q = t / a.nb, b = t - q * a.nb;             // tickets run block-major: (q, b-1) is always taken before (q, b)
+    int q, b;                                             // (q, b-1) and the unit left of (q, b) are always taken before (q, b)
+    if (a.order != nullptr) { const int2 o = __ldg(a.order + t); q = o.x; b = o.y; }
+    else { q = t / a.nb; b = t - q * a.nb; }              // block-major
     const int gb = q * a.world + a.rank;                  // global column block
     const long long c0 = (long long)gb * a.wc;            // its first column
     const int m = (int)((a.m - c0 < a.wc) ? a.m - c0 : a.wc);

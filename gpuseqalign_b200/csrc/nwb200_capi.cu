@@ -109,6 +109,15 @@ int launch_fill(nwb200_ctx* c, const FillArgs& a)
     int per_sm = 16 / g.W; if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     if (grid > ctas_needed) grid = ctas_needed;
+    if (a.order != nullptr) {
+        // column-block wavefront: one unit per band is runnable at any time (on ONE of the ranks); warps beyond that only hold tickets and
+        // poll, on the schedulers of the warps that work.  Window = this rank's share of the bands + half as many again for the hand-overs.
+        long long window = ((long long)g.nb + a.world - 1) / a.world;
+        window += window / 2 + 32;
+        if (const char* e = getenv("NWB200_WAVE_WARPS")) { const long long v = atoll(e); if (v > 0) window = v; }      // developer switch
+        const long long cap = (window + g.W - 1) / g.W;
+        if (grid > cap) grid = cap;
+    }
     grid -= grid % cluster;
     if (grid < cluster) grid = cluster;
 #define NWB_CASE(R_, K_, W_) if (g.R == R_ && g.K == K_ && g.W == W_) return launch_fill_t<R_, K_, W_>(c, a, (int)grid, cluster)
@@ -152,7 +161,7 @@ void nwb200_destroy(nwb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
-    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync,
+    for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync, &c->d_order,
                       &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
                       &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})
         b->release();
@@ -285,7 +294,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     a.lastcol = nullptr; a.timeout_ns = 0; a.err = nullptr;
     c->epoch++;
     if (c->epoch == 0) c->epoch = 1;
-    a.tag = c->epoch; a.xtag = 0; a.ticket = c->d_sync.as<int>();
+    a.tag = c->epoch; a.xtag = 0; a.ticket = c->d_sync.as<int>(); a.order = nullptr;
     a.nb = g.nb; a.pad = g.pad;
     a.pd = 2; a.negg = -c->gap; a.map = nullptr;
     // the origin maps of the traceback ride along in the fill launch while every unit still gets an SM sub-partition of its own
