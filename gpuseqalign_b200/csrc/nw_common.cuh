@@ -64,10 +64,11 @@ __device__ __forceinline__ void st_relaxed64(unsigned long long* p, unsigned lon
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-// the same element written as two 32-bit halves in one 8-byte store (no 64-bit packing arithmetic in front of the store)
+// the same element from its two 32-bit halves: ONE naturally aligned 64-bit store (single-copy atomic: value and tag arrive together;
+// a .v2.u32 store is two 32-bit accesses in unspecified order as far as the memory model goes).  mov.b64 packs a register pair: no arithmetic.
 __device__ __forceinline__ void st_tagged(unsigned long long* p, int v, unsigned tag)
 {
-    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"((unsigned)v), "r"(tag) : "memory");
+    asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%1, %2};\n\tst.relaxed.gpu.global.u64 [%0], t;\n\t}" ::"l"(p), "r"((unsigned)v), "r"(tag) : "memory");
 }
 // Set when a wait for a tagged element gave up (a producer that never publishes must not hang the GPU): the host
 // reports errorInvalidResult.  ~2^21 polls of >= 20 ns + an L2 round trip each are several seconds.

@@ -287,15 +287,18 @@ __device__ __forceinline__ int4 ring_wait(unsigned addr)
     do {
         v = lds_volatile4(addr);
         if (++polls > (1u << 22)) { g_wait_timeout = 1; v = make_int4(0, 0, 0, 0); }
-    } while (__any_sync(kFull, v.w < 0));
+    } while (__any_sync(kFull, (v.x | v.y | v.z | v.w) < 0));
     return v;
 }
+// A quad is its own ready flag: an EMPTY slot holds -1 in ALL FOUR words and P >= 0 everywhere, so a quad is complete exactly when
+// none of its words is negative.  (The producer's 16-byte store -- possibly into another CTA's shared memory -- is not promised to
+// be single-copy atomic: checking one word only would let a torn store pass with stale words of the previous lap.)
 // complete read of one quad: wait for the producer, then hand the slot back as empty
 __device__ __forceinline__ int4 ring_take(unsigned addr)
 {
     int4 v = lds_volatile4(addr);
-    if (__any_sync(kFull, v.w < 0)) v = ring_wait(addr);
-    sts_volatile1(addr + 12, -1);
+    if (__any_sync(kFull, (v.x | v.y | v.z | v.w) < 0)) v = ring_wait(addr);
+    sts_volatile4(addr, -1, -1, -1, -1);
     return v;
 }
 constexpr int kRingQG = 2;      // quads per readiness check of a hand-off ring
@@ -402,15 +405,16 @@ __device__ __forceinline__ void sweep_chunk(Lane<R, MODE>& st, const int lane, c
                 const unsigned a0 = io.hin_s + 16u * (j0 - 1);
                 // EVERY quad of the group is checked and handed back (not only the last one): stores into another CTA's shared
                 // memory are not promised to arrive in program order
-                int any_w = qq[0].w;
+                // ... and ALL FOUR words of a quad: a torn 16-byte store must not pass with stale words (see ring_take)
+                int any_w = qq[0].x | qq[0].y | qq[0].z | qq[0].w;
 #pragma unroll
-                for (int q = 1; q < QG; q++) any_w |= qq[q].w;
+                for (int q = 1; q < QG; q++) any_w |= qq[q].x | qq[q].y | qq[q].z | qq[q].w;
                 if (__any_sync(kFull, any_w < 0)) {
 #pragma unroll
                     for (int q = 0; q < QG; q++) qq[q] = ring_wait(a0 + 16u * q);
                 }
 #pragma unroll
-                for (int q = 0; q < QG; q++) sts_volatile1(a0 + 16u * q + 12u, minus1);
+                for (int q = 0; q < QG; q++) sts_volatile4(a0 + 16u * q, minus1, minus1, minus1, minus1);
 #pragma unroll
                 for (int q = 0; q < QG; q++) {
                     const int e0 = 4 * (j0 + q) - L4;

@@ -283,7 +283,7 @@ int nwb200_fill_resident(nwb200_ctx* c, int flags)
     CU(c, c->d_sync.ensure(sizeof(int) * 8), NWB200_ERR_MEMORY_ALLOCATION, "alloc ticket");
     CU(c, cudaEventRecord(c->ev[2], c->stream), NWB200_ERR_CUDA_GENERAL, "event");
     CU(c, cudaMemsetAsync(c->d_sync.p, 0, sizeof(int) * 8, c->stream), NWB200_ERR_CUDA_GENERAL, "memset ticket");
-    FillArgs a;
+    FillArgs a = {};
     a.y = c->d_y.as<uint8_t>(); a.x = (c->d_y.as<uint8_t>() + c->x_off); a.n = g.n; a.m = g.m;
     a.sprime = c->d_sprime.as<uint8_t>(); a.S = c->S;
     a.HR = c->d_HR.as<unsigned long long>(); a.ldr = g.ldr;

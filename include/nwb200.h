@@ -177,8 +177,8 @@ NWB200_API int  nwb200_wave_connect(nwb200_ctx* ctx, const void* right_peer_hand
 NWB200_API int  nwb200_wave_fill(nwb200_ctx* ctx, unsigned epoch);           /* async on the ctx stream */
 NWB200_API int  nwb200_wave_fetch(nwb200_ctx* ctx, int* has_score, int32_t* align_cost);   /* syncs */
 
-/* Few rows x very many columns (BASELINE config 4): the row-parallel prefix-max scorer, one CTA per chunk of 4096
- * columns, one int per row crossing each chunk (and GPU) boundary.  Score only.  Multi-GPU use follows the wavefront
+/* Few rows x very many columns (BASELINE config 4): the row-parallel prefix-max scorer, one warp per strip of 512
+ * columns (groups of 16 strips dealt to the ranks), one int per row crossing each strip (and GPU) boundary.  Score only.  Multi-GPU use follows the wavefront
  * protocol: nwb200_scan_upload -> nwb200_wave_export -> nwb200_wave_connect -> [barrier] -> nwb200_scan_fill -> nwb200_scan_fetch. */
 NWB200_API int  nwb200_scan_upload(nwb200_ctx* ctx, const uint8_t* y, int64_t len_y, const uint8_t* x, int64_t len_x, int rank, int world);
 NWB200_API int  nwb200_scan_fill(nwb200_ctx* ctx, unsigned epoch);           /* async on the ctx stream */
