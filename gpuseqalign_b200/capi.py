@@ -52,6 +52,12 @@ class _Timing(C.Structure):
                 ("trace_calc", C.c_float), ("trace_cpy_host", C.c_float)]
 
 
+class _MemUsage(C.Structure):
+    _fields_ = [("device_bytes", C.c_uint64), ("pinned_host_bytes", C.c_uint64), ("shared_bytes", C.c_uint64), ("local_bytes", C.c_uint64),
+                ("register_bytes", C.c_uint64), ("regs_per_thread", C.c_int32), ("threads_per_block", C.c_int32), ("blocks", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 @dataclass
 class Params:
     rows_per_lane: int = 0
@@ -86,6 +92,7 @@ EXPORTS = [
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
     "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
+    "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
 ]
 
 _lib = None
@@ -132,6 +139,11 @@ def load_library():
     L.nwb200_kernel_launches.argtypes = [vp]
     L.nwb200_version.restype = C.c_char_p
     L.nwb200_batch_kernel_name.argtypes = [vp]; L.nwb200_batch_kernel_name.restype = C.c_char_p
+    L.nwb200_upload_pair_i32.argtypes = [vp, P(i32), i64, P(i32), i64, P(_Params)]
+    L.nwb200_get_hdr_info.argtypes = [vp, P(_HdrInfo)]
+    L.nwb200_score_rows.argtypes = [vp, i64, i64, vp]
+    L.nwb200_trace_values.argtypes = [vp, vp, C.c_size_t, P(C.c_size_t)]
+    L.nwb200_get_memory_usage.argtypes = [vp, P(_MemUsage)]
     L.nwb200_wave_upload.argtypes = [vp, vp, i64, vp, i64, P(_Params), C.c_int, C.c_int, C.c_int]
     L.nwb200_wave_export.argtypes = [vp, vp]
     L.nwb200_wave_connect.argtypes = [vp, vp]
@@ -233,6 +245,25 @@ class Engine:
         hcol = np.empty(self.info.hcol_elems, dtype=np.int32)
         self._check(self._L.nwb200_copy_headers(self._h, _ptr(hrow), _ptr(hcol)))
         return hrow, hcol
+
+    def score_rows(self, row0: int, nrows: int, adjcols: int) -> np.ndarray:
+        """Rows [row0, row0 + nrows) of the full score matrix (NwPrintScore's data), shape (nrows, adjcols)."""
+        out = np.empty((nrows, adjcols), dtype=np.int32)
+        self._check(self._L.nwb200_score_rows(self._h, row0, nrows, _ptr(out)))
+        return out
+
+    def trace_values(self) -> np.ndarray:
+        """calcDebugTrace: score-matrix values along the path, top-left -> bottom-right (after trace())."""
+        n = C.c_size_t(0)
+        self._L.nwb200_trace_values(self._h, None, 0, C.byref(n))
+        out = np.empty(n.value, dtype=np.int32)
+        self._check(self._L.nwb200_trace_values(self._h, _ptr(out), out.size, C.byref(n)))
+        return out
+
+    def memory_usage(self) -> dict:
+        m = _MemUsage()
+        self._check(self._L.nwb200_get_memory_usage(self._h, C.byref(m)))
+        return {k: getattr(m, k) for k, _ in _MemUsage._fields_ if k != "reserved"}
 
     def score_hash(self) -> int:
         h = C.c_uint32(0)

@@ -130,6 +130,9 @@ struct nwb200_ctx {
     unsigned epoch = 0;
     int launches = 0;
     const char* batch_kernel = "";
+    // resources of the last fill launch (nwb200_get_memory_usage; the reference's updateNwAlgPeakMemUsage, nwalign_shared.cpp:5-25)
+    int fill_regs = 0, fill_threads = 0, fill_blocks = 0;
+    size_t fill_smem_static = 0, fill_smem_dynamic = 0, fill_local = 0;
     cudaError_t last_cuda = cudaSuccess;
     std::string last_error;
 };

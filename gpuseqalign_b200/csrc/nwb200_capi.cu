@@ -89,6 +89,16 @@ int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
     }
     c->launches++;
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "fill kernel launch", e);
+    {
+        static cudaFuncAttributes at_dev[64];
+        static bool have[64] = {};
+        if (!have[c->device & 63]) { have[c->device & 63] = cudaFuncGetAttributes(&at_dev[c->device & 63], nw_fill_kernel<R, K, W>) == cudaSuccess; (void)cudaGetLastError(); }
+        if (have[c->device & 63]) {
+            const cudaFuncAttributes& at = at_dev[c->device & 63];
+            c->fill_regs = at.numRegs; c->fill_smem_static = at.sharedSizeBytes; c->fill_local = at.localSizeBytes;
+        }
+        c->fill_threads = W * 32; c->fill_blocks = grid; c->fill_smem_dynamic = smem;
+    }
     return NWB200_SUCCESS;
 }
 
@@ -266,6 +276,11 @@ static int upload_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, 
     return upload_common(c, sy, n, sx, m, p);
 }
 
+int nwb200_upload_pair_i32(nwb200_ctx* c, const int32_t* seqY, int64_t adjrows, const int32_t* seqX, int64_t adjcols, const nwb200_params* p)
+{
+    return upload_pair_i32(c, seqY, adjrows, seqX, adjcols, p);
+}
+
 int nwb200_fill_resident(nwb200_ctx* c, int flags)
 {
     if (!c || !c->pair_resident) return fail(c, NWB200_ERR_INVALID_VALUE, "no pair resident on the device");
@@ -375,6 +390,13 @@ static void fill_hdr_info(const nwb200_ctx* c, nwb200_hdr_info* h)
     h->hcol_elems = (int64_t)g.nb * g.tcols * (1 + g.By);
 }
 
+int nwb200_get_hdr_info(const nwb200_ctx* c, nwb200_hdr_info* hdr)
+{
+    if (!c || !hdr || !c->pair_resident) return NWB200_ERR_INVALID_VALUE;
+    fill_hdr_info(c, hdr);
+    return NWB200_SUCCESS;
+}
+
 static int enqueue_moves_copy(nwb200_ctx* c);
 
 int nwb200_align_pair_u8(nwb200_ctx* c, const uint8_t* y, int64_t n, const uint8_t* x, int64_t m,
@@ -454,6 +476,21 @@ int nwb200_sync(nwb200_ctx* c)
     return NWB200_SUCCESS;
 }
 int nwb200_kernel_launches(const nwb200_ctx* c) { return c ? c->launches : 0; }
+int nwb200_get_memory_usage(const nwb200_ctx* c, nwb200_mem_usage* out)
+{
+    if (!c || !out) return NWB200_ERR_INVALID_VALUE;
+    memset(out, 0, sizeof(*out));
+    for (const DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync, &c->d_order,
+                            &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
+                            &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})
+        out->device_bytes += b->cap;
+    for (const PinBuf* b : {&c->h_stage, &c->h_small, &c->h_trace, &c->h_batch, &c->h_export, &c->h_bscores, &c->h_bmoves}) out->pinned_host_bytes += b->cap;
+    out->regs_per_thread = c->fill_regs; out->threads_per_block = c->fill_threads; out->blocks = c->fill_blocks;
+    out->shared_bytes = (uint64_t)(c->fill_smem_static + c->fill_smem_dynamic) * (uint64_t)c->fill_blocks;
+    out->local_bytes = (uint64_t)c->fill_local * (uint64_t)c->fill_threads * (uint64_t)c->fill_blocks;
+    out->register_bytes = (uint64_t)c->fill_regs * 4u * (uint64_t)c->fill_threads * (uint64_t)c->fill_blocks;
+    return NWB200_SUCCESS;
+}
 const char* nwb200_batch_kernel_name(const nwb200_ctx* c) { return c ? c->batch_kernel : ""; }
 
 }  // extern "C"

@@ -17,6 +17,11 @@
 #include "nwalign_shared.hpp"
 #include "nwb200.h"
 
+#include "fmt_guard.hpp"
+
+#include <algorithm>
+#include <iomanip>
+#include <string>
 #include <vector>
 
 namespace {
@@ -67,38 +72,68 @@ NwStat NwAlign_B200(const NwAlgParams& pr, NwAlgInput& nw, NwAlgResult& res)
     p.tile_cols = param_or_zero(pr, "tileCols");
     p.reserved = param_or_zero(pr, "skew");
 
-    int cost = 0;
-    nwb200_hdr_info info;
-    int rc = nwb200_align_pair_i32(e.ctx, nw.seqY.data(), nw.adjrows, nw.seqX.data(), nw.adjcols, &p, NWB200_KEEP_HEADERS, &cost, &info);
-    if (rc != NWB200_SUCCESS) {
+    // The phases are separate C-ABI calls, each ending in a synchronisation, so that the Stopwatch laps are the reference's own
+    // (nwalign_gpu9_mlsp_diagdiagdiag.cu:481 "align.cpy_dev", :687 "align.calc", :711 "align.cpy_host"; file_formats.cpp:505-510).
+    auto failed = [&](int rc) {
         res.cudaStat = static_cast<cudaError_t>(nwb200_last_cuda_error(e.ctx));
         return to_stat(rc);
-    }
+    };
+    int rc = nwb200_upload_pair_i32(e.ctx, nw.seqY.data(), nw.adjrows, nw.seqX.data(), nw.adjcols, &p);
+    if (rc == NWB200_SUCCESS) rc = nwb200_sync(e.ctx);
+    if (rc != NWB200_SUCCESS) return failed(rc);
+    res.sw_align.lap("align.cpy_dev");
+
+    rc = nwb200_fill_resident(e.ctx, NWB200_KEEP_HEADERS);
+    if (rc == NWB200_SUCCESS) rc = nwb200_sync(e.ctx);
+    if (rc != NWB200_SUCCESS) return failed(rc);
+    res.sw_align.lap("align.calc");
+
+    int cost = 0;
+    rc = nwb200_fetch_score(e.ctx, &cost);
+    if (rc != NWB200_SUCCESS) return failed(rc);
     res.align_cost = cost;
+    res.sw_align.lap("align.cpy_host");
+
     // publish the sparse geometry like gpu9 does (nwalign_gpu9_mlsp_diagdiagdiag.cu:696-699); lengths >= 2 keep the
     // reference's NwTrace2_GetTileAndElemIJ well defined should someone pair this align with NwHash2_Sparse
-    nw.tileHdrMatRows = info.trows;
-    nw.tileHdrMatCols = info.tcols;
-    nw.tileHrowLen = 1 + info.tile_cols;
-    nw.tileHcolLen = 1 + info.tile_rows;
-    // device-side phase times of the engine (CUDA events), reported under the reference's lap names
-    nwb200_timing t;
-    nwb200_get_timing(e.ctx, &t);
-    res.sw_align.lap("align.calc");
+    nwb200_hdr_info info;
+    if (nwb200_get_hdr_info(e.ctx, &info) == NWB200_SUCCESS) {
+        nw.tileHdrMatRows = info.trows;
+        nw.tileHdrMatCols = info.tcols;
+        nw.tileHrowLen = 1 + info.tile_cols;
+        nw.tileHcolLen = 1 + info.tile_rows;
+    }
+    // peak memory: host allocations of NwAlgInput as every algorithm reports them, and the engine's own device buffers and launch
+    // resources in the places where the reference's kernels report theirs (nwalign_shared.cpp:16-24; the engine's buffers live
+    // in its context, not in NwAlgInput, so measureDeviceAllocations() does not see them)
     updateNwAlgPeakMemUsage(nw, res);
+    nwb200_mem_usage mu;
+    if (nwb200_get_memory_usage(e.ctx, &mu) == NWB200_SUCCESS) {
+        res.ramPeakAllocs = std::max<size_t>(res.ramPeakAllocs, nw.measureHostAllocations() + (size_t)mu.pinned_host_bytes);
+        res.globalMemPeakAllocs = std::max<size_t>(res.globalMemPeakAllocs, nw.measureDeviceAllocations() + (size_t)mu.device_bytes);
+        res.sharedMemPeakAllocs = std::max<size_t>(res.sharedMemPeakAllocs, (size_t)mu.shared_bytes);
+        res.localMemPeakAllocs = std::max<size_t>(res.localMemPeakAllocs, (size_t)mu.local_bytes);
+        res.regMemPeakAllocs = std::max<size_t>(res.regMemPeakAllocs, (size_t)mu.register_bytes);
+    }
     return NwStat::success;
 }
 
 NwStat NwTrace_B200(NwAlgInput& nw, NwAlgResult& res, bool calcDebugTrace)
 {
-    (void)nw;
     Engine& e = engine();
     if (!e.ctx) return NwStat::errorInvalidValue;
-    if (calcDebugTrace) return NwStat::errorInvalidValue;      // the cell values along the path are not materialised (only with --fPrintTrace)
     res.sw_trace.start();
     size_t len = 0;
     uint32_t hash = 0;
-    std::string buf((size_t)nw.adjrows + (size_t)nw.adjcols + 64, '\0');
+    std::string buf;
+    try {
+        buf.assign((size_t)nw.adjrows + (size_t)nw.adjcols + 64, '\0');
+        if (calcDebugTrace) nw.trace.reserve((size_t)nw.adjrows - 1 + (size_t)nw.adjcols);      // nwtrace1_plain.cpp:15-18
+    } catch (const std::exception&) {
+        return NwStat::errorMemoryAllocation;
+    }
+    updateNwAlgPeakMemUsage(nw, res);
+    res.sw_trace.lap("trace.alloc");
     int rc = nwb200_trace_pair(e.ctx, &buf[0], buf.size(), &len, &hash);
     if (rc == NWB200_ERR_INVALID_VALUE && len > buf.size()) {
         buf.resize(len);
@@ -110,8 +145,21 @@ NwStat NwTrace_B200(NwAlgInput& nw, NwAlgResult& res, bool calcDebugTrace)
     }
     buf.resize(len);
     res.edit_trace = std::move(buf);
-    res.trace_hash = hash;
     res.sw_trace.lap("trace.calc");
+    if (calcDebugTrace) {
+        // the score-matrix values along the path, top-left -> bottom-right, folded into the hash behind the transcript
+        // (nwtrace1_plain.cpp:34-38,107,120-126)
+        size_t cnt = 0;
+        nwb200_trace_values(e.ctx, nullptr, 0, &cnt);
+        try { nw.trace.assign(cnt, 0); } catch (const std::exception&) { return NwStat::errorMemoryAllocation; }
+        rc = nwb200_trace_values(e.ctx, nw.trace.data(), nw.trace.size(), &cnt);
+        if (rc != NWB200_SUCCESS) {
+            res.cudaStat = static_cast<cudaError_t>(nwb200_last_cuda_error(e.ctx));
+            return to_stat(rc);
+        }
+        for (auto& curr : nw.trace) hash = ((hash << 5) + hash) ^ (unsigned)curr;
+    }
+    res.trace_hash = hash;
     return NwStat::success;
 }
 
@@ -132,9 +180,29 @@ NwStat NwHash_B200(NwAlgInput& nw, NwAlgResult& res)
     return NwStat::success;
 }
 
+// The score matrix in the reference's text form (print_mat.hpp / NwPrintScore2_Sparse, nwtrace2_sparse.cpp:346-419: every element
+// setw(4) and a comma, one matrix row per line); the rows are recomputed on the GPU a block at a time.
 NwStat NwPrintScore_B200(std::ostream& os, const NwAlgInput& nw, NwAlgResult& res)
 {
-    (void)nw; (void)res;
-    os << "(score matrix is not materialised by NwAlign_B200: only band header rows live in HBM)\n";
+    Engine& e = engine();
+    if (!e.ctx) return NwStat::errorInvalidValue;
+    FormatFlagsGuard fg {os, 4};
+    const long long rows = nw.adjrows, cols = nw.adjcols;
+    const long long block = std::max<long long>(1, (long long)(16 << 20) / std::max<long long>(cols, 1));      // ~64 MB of ints at a time
+    std::vector<int> buf;
+    try { buf.resize((size_t)std::min(block, rows) * (size_t)cols); } catch (const std::exception&) { return NwStat::errorMemoryAllocation; }
+    updateNwAlgPeakMemUsage(nw, res);
+    for (long long r0 = 0; r0 < rows; r0 += block) {
+        const long long k = std::min(block, rows - r0);
+        int rc = nwb200_score_rows(e.ctx, r0, k, buf.data());
+        if (rc != NWB200_SUCCESS) {
+            res.cudaStat = static_cast<cudaError_t>(nwb200_last_cuda_error(e.ctx));
+            return to_stat(rc);
+        }
+        for (long long i = 0; i < k; i++) {
+            for (long long j = 0; j < cols; j++) os << std::setw(4) << buf[(size_t)(i * cols + j)] << ',';
+            os << '\n';
+        }
+    }
     return NwStat::success;
 }

@@ -94,6 +94,17 @@ typedef struct nwb200_timing {
     float trace_cpy_host;  /* D2H of the transcript                    */
 } nwb200_timing;
 
+/* Resources of the context and of its last fill launch: what updateNwAlgPeakMemUsage collects from cudaFuncAttributes x
+ * active blocks for the reference's kernels (nwalign_shared.cpp:5-25). */
+typedef struct nwb200_mem_usage {
+    uint64_t device_bytes;        /* device buffers owned by the context (letters, header rows, snapshots, maps, batch buffers ...) */
+    uint64_t pinned_host_bytes;   /* pinned staging buffers                                                                       */
+    uint64_t shared_bytes;        /* (static + dynamic shared memory per CTA) x CTAs of the last fill launch                      */
+    uint64_t local_bytes;         /* local memory per thread x threads x CTAs                                                      */
+    uint64_t register_bytes;      /* registers per thread x 4 x threads x CTAs                                                     */
+    int32_t  regs_per_thread, threads_per_block, blocks, reserved;
+} nwb200_mem_usage;
+
 NWB200_API int  nwb200_create(nwb200_ctx** out, int device);
 NWB200_API void nwb200_destroy(nwb200_ctx* ctx);
 
@@ -118,6 +129,9 @@ NWB200_API int  nwb200_align_pair_u8(nwb200_ctx* ctx, const uint8_t* y, int64_t 
  * upload once, then (re)run fill / trace any number of times. */
 NWB200_API int  nwb200_upload_pair_u8(nwb200_ctx* ctx, const uint8_t* y, int64_t len_y,
                                       const uint8_t* x, int64_t len_x, const nwb200_params* params);
+NWB200_API int  nwb200_upload_pair_i32(nwb200_ctx* ctx, const int32_t* seqY, int64_t adjrows,
+                                       const int32_t* seqX, int64_t adjcols, const nwb200_params* params);
+NWB200_API int  nwb200_get_hdr_info(const nwb200_ctx* ctx, nwb200_hdr_info* hdr); /* geometry of the resident pair */
 NWB200_API int  nwb200_fill_resident(nwb200_ctx* ctx, int flags);            /* async on the ctx stream */
 NWB200_API int  nwb200_trace_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
 NWB200_API int  nwb200_fetch_score(nwb200_ctx* ctx, int32_t* align_cost);    /* syncs */
@@ -142,6 +156,15 @@ NWB200_API int  nwb200_copy_headers(nwb200_ctx* ctx, int32_t* hrow_host, int32_t
  * rows are recomputed on the GPU in slabs from the device-resident sequences and folded on
  * the host as they stream back. */
 NWB200_API int  nwb200_score_hash(nwb200_ctx* ctx, uint32_t* score_hash);
+
+/* Replaces NwPrintScore2_Sparse's row recomputation (nwtrace2_sparse.cpp:346-419): rows [row0, row0 + nrows) of the
+ * full score matrix, adjcols = lenX + 1 ints per row (row 0 / column 0 included), recomputed on the GPU. */
+NWB200_API int  nwb200_score_rows(nwb200_ctx* ctx, int64_t row0, int64_t nrows, int32_t* out);
+
+/* calcDebugTrace (nwtrace1_plain.cpp:34-38,107,120-126): the score-matrix values along the traceback path, top-left ->
+ * bottom-right, both corners included (*count = moves + 1; NWB200_ERR_INVALID_VALUE with *count set when cap is too
+ * small).  Call after nwb200_trace_pair / nwb200_fetch_trace.  O(matrix) work: a debugging aid for small pairs. */
+NWB200_API int  nwb200_trace_values(nwb200_ctx* ctx, int32_t* values, size_t cap, size_t* count);
 
 /* Batch of independent pairs (BASELINE config 3): byte letters in one pool, per-pair
  * offsets/lengths.  scores[n_pairs] always; if edits != NULL each pair's transcript is written
@@ -191,6 +214,7 @@ NWB200_API int         nwb200_get_timing(const nwb200_ctx* ctx, nwb200_timing* o
 NWB200_API void*       nwb200_stream(const nwb200_ctx* ctx);                 /* cudaStream_t */
 NWB200_API int         nwb200_sync(nwb200_ctx* ctx);
 NWB200_API int         nwb200_kernel_launches(const nwb200_ctx* ctx);        /* kernels launched so far */
+NWB200_API int         nwb200_get_memory_usage(const nwb200_ctx* ctx, nwb200_mem_usage* out);
 NWB200_API const char* nwb200_batch_kernel_name(const nwb200_ctx* ctx);      /* kernel the last batch launch used ("" before one) */
 NWB200_API const char* nwb200_version(void);
 

@@ -108,6 +108,14 @@ def align_pair(y: np.ndarray, x: np.ndarray, subst: np.ndarray, gap: int, *, wan
                       edit=buf.raw[: elen.value].decode("ascii") if want_trace else None)
 
 
+def fill_full(y: np.ndarray, x: np.ndarray, subst: np.ndarray, gap: int) -> np.ndarray:
+    """The whole score matrix H, shape (len(y) + 1, len(x) + 1) (cpu1 restatement, nwalign_cpu1_st_row.cpp:39-62)."""
+    sy, sx = _hdr(y), _hdr(x)
+    H = np.zeros((sy.size, sx.size), dtype=np.int32)
+    lib().nwo_fill_full(sy, sy.size, sx, sx.size, np.ascontiguousarray(subst, dtype=np.int32), int(round(len(subst) ** 0.5)), gap, H.reshape(-1))
+    return H
+
+
 def fill_rolling(y: np.ndarray, x: np.ndarray, subst: np.ndarray, gap: int, By: int = 0, Bx: int = 0,
                  want_hash: bool = False):
     """Rolling-row oracle: returns (score, hrow, hcol, score_hash); headers in the App. A-4 layout when By,Bx > 0."""

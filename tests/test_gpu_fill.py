@@ -198,6 +198,47 @@ def test_score_hash_multi_band_and_variants(engine, scoring, oracle):
         assert engine.score_hash() == exp.score_hash
 
 
+def _path_cells(edit: str, n: int, m: int):
+    """Cells of the path described by a run-length transcript, top-left -> bottom-right."""
+    import re
+    i = j = 0
+    cells = [(0, 0)]
+    for cnt, op in re.findall(r"(\d*)([=XID])", edit):
+        for _ in range(int(cnt) if cnt else 1):
+            if op in "=X": i += 1; j += 1
+            elif op == "I": i += 1
+            else: j += 1
+            cells.append((i, j))
+    assert (i, j) == (n, m)
+    return cells
+
+
+def test_score_rows_path_values_and_memory_usage(engine, scoring, oracle):
+    """The calls behind the plugin's NwPrintScore / calcDebugTrace / peak-memory columns: rows of the full score matrix recomputed
+    on the GPU (nwtrace2_sparse.cpp:346-419), the matrix values along the path (nwtrace1_plain.cpp:34-38,107,120-126), and the
+    launch resources (nwalign_shared.cpp:5-25)."""
+    from gpuseqalign_b200 import Params, synth
+    subst = scoring["subst"]["blosum62"]
+    for (n, m, p) in ((1333, 1900, None), (77, 3, None), (1, 1, None), (700, 2100, Params(4, 1, 32, 2)), (2500, 301, Params(8, 4, 256, 1))):
+        x = synth.letters(900 + n, m); y = synth.mutated_copy(x, 901 + m, n) if n > 3 else synth.letters(5, n)
+        H = oracle.fill_full(y, x, subst, -11)
+        assert engine.align(y, x, keep_headers=True, params=p) == H[-1, -1]
+        assert np.array_equal(engine.score_rows(0, n + 1, m + 1), H)
+        for (r0, k) in ((0, 1), (n, 1), (n // 2, min(3, n + 1 - n // 2)), (1, 0)):
+            assert np.array_equal(engine.score_rows(r0, k, m + 1), H[r0:r0 + k])
+        edit, th = engine.trace()
+        vals = engine.trace_values()
+        cells = _path_cells(edit, n, m)
+        assert np.array_equal(vals, np.array([H[i, j] for i, j in cells], dtype=np.int32))
+        assert engine.trace() == (edit, th)                                  # the value pass leaves the cached transcript intact
+        mu = engine.memory_usage()
+        assert mu["device_bytes"] > 0 and mu["regs_per_thread"] > 0 and mu["blocks"] > 0
+        assert mu["register_bytes"] == mu["regs_per_thread"] * 4 * mu["threads_per_block"] * mu["blocks"]
+        assert mu["shared_bytes"] > 0
+    with pytest.raises(Exception):
+        engine.score_rows(n, 5, m + 1)
+
+
 @pytest.mark.parametrize("R,Bx", [(4, 64), (8, 96), (4, 512)])
 def test_exported_headers_feed_reference_style_trace(engine, golden, scoring, oracle, R, Bx):
     """nwb200_copy_headers: headers in the reference's tile layout must let NwTrace2_Sparse (restated, and the live

@@ -187,3 +187,47 @@ def test_reference_benchmark_executable_accepts_the_plugin():
     b200 = [dict(zip(hdr, r_)) for r_ in rows[1:] if r_[0] == "NwAlign_B200"]
     assert len(b200) == 173
     assert all(r_["err_step"] == "0" for r_ in b200)
+
+
+def test_reference_benchmark_debug_output_with_the_plugin():
+    """--fPrintTrace / --fPrintScore through the reference's executable: calcDebugTrace folds the path's matrix values into
+    trace_hash (nwtrace1_plain.cpp:120-126), so exit code 0 means NwTrace_B200's values equal NwTrace1_Plain's; the printed trace
+    of the B200 entry equals cpu4's text byte for byte, its score matrix equals gpu9's (NwPrintScore2_Sparse, nwtrace2_sparse.cpp:346-419:
+    setw(4) and a comma) byte for byte and cpu4's (NwPrintScore1_Plain: setw(4) and a blank) value for value."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "nw_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/nw_b200 was not prebuilt")
+    outdir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(outdir, exist_ok=True)
+    pairs = os.path.join(outdir, "test_pairs_debug_small.txt")
+    with open(pairs, "w") as f:
+        f.write("len1 len1\nlen1 len33\nlen66 len1\nlen40 len60\nlen256 len196\nlen500 len1000\n")
+    out = os.path.join(outdir, "test_ref_bench_debug.tsv")
+    dbg = os.path.join(outdir, "test_ref_bench_debug.txt")
+    r = subprocess.run([exe, "-b", "resrc/subst.json", "-r", os.path.join(ROOT, "gpuseqalign_b200", "plugin", "param_b200.json"),
+                        "-s", "resrc/seq_generated.fa", "-p", pairs, "--fCalcTrace", "--fCalcScoreHash", "--fPrintTrace", "--fPrintScore",
+                        "--debugPath", dbg, "-o", out],
+                       cwd=os.path.join(ROOT, "oracle", "_ref"), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    blocks = [b for b in open(dbg).read().split(">results\n") if b.strip()]
+    by_alg = {}
+    for b in blocks:
+        head, _, rest = b.partition("+\n>edit_trace\n")
+        cols = head.splitlines()[0].split("\t"); vals = head.splitlines()[1].split("\t")
+        row = dict(zip(cols, vals))
+        trace_txt, _, score_txt = rest.partition("+\n>score_matrix\n")
+        by_alg.setdefault(row["alg_name"], []).append((row["seqY_idx"], row["seqX_idx"], row["trace_hash"], trace_txt, score_txt))
+    ref = by_alg["NwAlign_Cpu4_Mt_DiagRow"]; gpu9 = by_alg["NwAlign_Gpu9_Mlsp_DiagDiagDiag"]; got = by_alg["NwAlign_B200"]
+    assert len(ref) == len(gpu9) == len(got) == 6
+    for a, g, b in zip(ref, gpu9, got):
+        assert a[:4] == b[:4]                                        # pair, trace hash (path values folded in), printed trace
+        assert g == b                                                # + the printed score matrix, byte for byte
+        assert a[4].replace(" \n", "\n").split() == b[4].replace(",", " ").split()
+    # peak-memory columns of the B200 rows are filled in (updateNwAlgPeakMemUsage's places, nwalign_shared.cpp:16-24)
+    rows = [l.split("\t") for l in open(out).read().splitlines()]
+    hdr = rows[0]
+    for r_ in rows[1:]:
+        d = dict(zip(hdr, r_))
+        if d["alg_name"] == "NwAlign_B200":
+            assert int(d["glmem_peak_allocs"]) > 0 and int(d["shmem_peak_allocs"]) > 0 and int(d["regmem_peak_allocs"]) > 0
+            assert float(d["align.cpy_dev"]) > 0 and float(d["align.cpy_host"]) > 0
