@@ -105,9 +105,15 @@ def test_batch_packed_and_32bit_kernels_agree(engine, scoring, oracle, monkeypat
     exp = oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11)
     monkeypatch.setenv("NWB200_BATCH_PACKED", "1")
     packed = engine.align_batch(letters, offY, lenY, offX, lenX)
+    assert np.array_equal(packed, exp)
+    # every packed instance: round 1's kernel (0), two pairs per warp (1: the 32-lane groups), mixed IDP routes (2), K = 2 (3),
+    # four pairs per warp (4: 16-lane groups, 16 rows per lane; 5: with K = 2; 6: split lanes), expanded profiles (7)
+    for v in ("0", "1", "2", "3", "4", "5", "6", "7"):
+        monkeypatch.setenv("NWB200_BATCH_VARIANT", v)
+        assert np.array_equal(engine.align_batch(letters, offY, lenY, offX, lenX), exp), v
+    monkeypatch.delenv("NWB200_BATCH_VARIANT")
     monkeypatch.setenv("NWB200_BATCH_PACKED", "0")
     plain = engine.align_batch(letters, offY, lenY, offX, lenX)
-    assert np.array_equal(packed, exp)
     assert np.array_equal(plain, exp)
 
 

@@ -1,3 +1,9 @@
-python -m pytest tests -m gpu -x -q > gpurun_out/r2p_tests.log 2>&1; echo tests rc=$?; tail -5 gpurun_out/r2p_tests.log
-( time python bench.py > gpurun_out/r2p_bench_default.json 2> gpurun_out/r2p_bench_default.err ) 2>&1 | tail -4; echo bench rc=$?
-tail -c 600 gpurun_out/r2p_bench_default.err
+python -m pytest tests/test_gpu_batch.py -m gpu -x -q 2>&1 | tail -3
+for v in 1 7; do
+NWB200_BATCH_VARIANT=$v python bench.py --steps 10 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/r2q_bench_v$v.json 2> gpurun_out/r2q_bench_v$v.err; echo rc=$?
+done
+python -c "
+import json
+for v in (1,7):
+    d=json.loads(open('gpurun_out/r2q_bench_v%d.json'%v).read().strip().splitlines()[-1]); print(v, d['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['kernel'], d['e2e']['value'], d.get('parity'))
+"

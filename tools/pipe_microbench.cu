@@ -35,6 +35,9 @@ enum Op {
     OP_MIX_PACKED2,        // two pairs per register: d = dp4a(wA, sel, diag) ; d = dp2a(wB, sel2, d) ; c = vimax3_u16x2(d, up, left)
     OP_MIX_MERGED2,        // round 2: m = prmt(wA, wB) per TWO rows ; d = dp2a_lo/hi(0x80000001, m, diag) ; c = vimax3_u16x2(d, up, left)
     OP_MIX_DP2A_MAX3_16,   // the same without the permute (the ceiling if the two profile words came pre-merged)
+    OP_MIX_ADDMERGE2,      // the merge as ONE integer add of two words with disjoint bytes (profiles stored two rows per word)
+    OP_MIX_LOPMERGE2,      // ... as a LOP3
+    OP_MIX_IMADMERGE2,     // ... as an IMAD (fma pipe)
     OP_COUNT
 };
 
@@ -46,7 +49,9 @@ static const char* op_names[OP_COUNT] = {
     "SHFL.UP", "LDS.32", "LDS.64", "LDS.128",
     "mix: 4x(IMAD+VIMNMX3)+SHFL (per 4 cells)", "mix: 4x(IMAD+VIMNMX3)+LDS32 (per 4 cells)",
     "IDP.2A", "mix16: IDP4A+IDP2A+VIMNMX3.U16x2 (per 2 cells)",
-    "mix16: 0.5 PRMT+IDP2A+VIMNMX3.U16x2 (per 2 cells)", "mix16: IDP2A+VIMNMX3.U16x2 (per 2 cells)"};
+    "mix16: 0.5 PRMT+IDP2A+VIMNMX3.U16x2 (per 2 cells)", "mix16: IDP2A+VIMNMX3.U16x2 (per 2 cells)",
+    "mix16: 0.5 IADD+IDP2A+VIMNMX3.U16x2 (per 2 cells)", "mix16: 0.5 LOP3+IDP2A+VIMNMX3.U16x2 (per 2 cells)",
+    "mix16: 0.5 IMAD+IDP2A+VIMNMX3.U16x2 (per 2 cells)"};
 
 // "units" per inner-loop body per accumulator (what the reported rate counts).
 template <int OP>
@@ -72,6 +77,19 @@ __device__ __forceinline__ void body(int (&a)[ILP], int (&b)[ILP], int p, int q,
         else if (OP == OP_MIX_MERGED2) {
             if ((k & 1) == 0) {
                 const unsigned m = __byte_perm((unsigned)p + (unsigned)b[k], (unsigned)q, (unsigned)sel);
+                unsigned d0 = __dp2a_lo(0x80000001u, m, (unsigned)b[k]);
+                unsigned d1 = __dp2a_hi(0x80000001u, m, (unsigned)b[k + 1]);
+                unsigned c0 = __vimax3_u16x2(d0, (unsigned)a[k], (unsigned)b[k]);
+                unsigned c1 = __vimax3_u16x2(d1, (unsigned)a[k + 1], (unsigned)b[k + 1]);
+                b[k] = a[k]; a[k] = c0; b[k + 1] = a[k + 1]; a[k + 1] = c1;
+            }
+        }
+        else if (OP == OP_MIX_ADDMERGE2 || OP == OP_MIX_LOPMERGE2 || OP == OP_MIX_IMADMERGE2) {
+            if ((k & 1) == 0) {
+                unsigned m;
+                if (OP == OP_MIX_ADDMERGE2) asm volatile("add.u32 %0, %1, %2;" : "=r"(m) : "r"((unsigned)b[k]), "r"((unsigned)q));
+                else if (OP == OP_MIX_LOPMERGE2) asm volatile("lop3.b32 %0, %1, %2, %3, 0xfe;" : "=r"(m) : "r"((unsigned)b[k]), "r"((unsigned)q), "r"((unsigned)p));
+                else asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(m) : "r"((unsigned)b[k]), "r"((unsigned)q), "r"((unsigned)p));
                 unsigned d0 = __dp2a_lo(0x80000001u, m, (unsigned)b[k]);
                 unsigned d1 = __dp2a_hi(0x80000001u, m, (unsigned)b[k + 1]);
                 unsigned c0 = __vimax3_u16x2(d0, (unsigned)a[k], (unsigned)b[k]);
@@ -243,6 +261,9 @@ int main() {
         run_tp<OP_MIX_PACKED2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
         run_tp<OP_MIX_MERGED2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
         run_tp<OP_MIX_DP2A_MAX3_16>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
+        run_tp<OP_MIX_ADDMERGE2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
+        run_tp<OP_MIX_LOPMERGE2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
+        run_tp<OP_MIX_IMADMERGE2>(d_out, d_cyc, sms, threads, 2 * ILP, "cells");
     }
     run_lat<OP_VIMNMX3>(d_out, d_cyc);
     run_lat<OP_VIADDMNMX>(d_out, d_cyc);
