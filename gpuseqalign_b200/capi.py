@@ -92,7 +92,7 @@ EXPORTS = [
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
     "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
-    "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
+    "nwb200_trace_info", "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def load_library():
     L.nwb200_score_rows.argtypes = [vp, i64, i64, vp]
     L.nwb200_trace_values.argtypes = [vp, vp, C.c_size_t, P(C.c_size_t)]
     L.nwb200_get_memory_usage.argtypes = [vp, P(_MemUsage)]
+    L.nwb200_trace_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
     L.nwb200_wave_upload.argtypes = [vp, vp, i64, vp, i64, P(_Params), C.c_int, C.c_int, C.c_int]
     L.nwb200_wave_export.argtypes = [vp, vp]
     L.nwb200_wave_connect.argtypes = [vp, vp]
@@ -259,6 +260,12 @@ class Engine:
         out = np.empty(n.value, dtype=np.int32)
         self._check(self._L.nwb200_trace_values(self._h, _ptr(out), out.size, C.byref(n)))
         return out
+
+    def trace_info(self) -> dict:
+        """Corridor diagnostics of the last traceback: segments per band in the corridor pass, segments per band, miss flag."""
+        cw, ns, miss = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._L.nwb200_trace_info(self._h, C.byref(cw), C.byref(ns), C.byref(miss)))
+        return {"corridor_segments": cw.value, "segments": ns.value, "corridor_missed": bool(miss.value)}
 
     def memory_usage(self) -> dict:
         m = _MemUsage()

@@ -52,7 +52,32 @@ struct TraceArgs {
     // cell got in segment j, its own left neighbour: the chase follows these until it meets a top-row column.
     int* cut;
     int nseg;
+    // ---- corridor maps (long pairs): pass A computes only the segments of a band within corr_d columns of the straight line from
+    // (n, m) to the origin -- corr_w segments per band instead of nseg -- and pass B checks every lookup against that range.  A path
+    // that leaves the corridor sets *miss; the full pass A and pass B, enqueued right behind (phase 1), then run -- they return at
+    // once otherwise.  The walkers check the result either way (exitj against entry).
+    int corr_w;                      // segments per band of the corridor pass; 0: no corridor
+    int corr_d;                      // half width of the corridor in columns
+    int phase;                       // 0: first pass (the corridor when corr_w > 0), 1: the full pass that runs only after a miss
+    int* miss;
 };
+
+// Segments [lo, hi] of band b that the corridor pass computes (every segment without a corridor).  Column c of a band's bottom row
+// comes out of chunk (c + lag) / 32, i.e. of segment (c + lag) / (32 snap_chunks).
+__host__ __device__ __forceinline__ void corridor_range(const TraceArgs& a, int b, int By, int lag, int& lo, int& hi)
+{
+    if (a.corr_w <= 0) { lo = 0; hi = a.nseg - 1; return; }
+    long long rb = (long long)(b + 1) * By - a.pad, rt = (long long)b * By - a.pad;      // matrix rows of the band's last row and of the row above its first
+    if (rb > a.n) rb = a.n;
+    if (rt < 0) rt = 0;
+    const long long per = 32LL * a.snap_chunks;
+    long long xlo = (long long)a.m * rt / a.n - a.corr_d, xhi = (long long)a.m * rb / a.n + a.corr_d;
+    if (xlo < 0) xlo = 0;
+    long long l = (xlo + lag) / per, h = (xhi + lag) / per;
+    if (h > a.nseg - 1) h = a.nseg - 1;
+    if (l > h) l = h;
+    lo = (int)l; hi = (int)h;
+}
 
 // Loads a plain (already complete) header-row group into the top-row ring.
 template <int R, int K>
@@ -87,9 +112,19 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     const long long nwarps = (long long)gridDim.x * WARPS;
     const int nseg = a.nseg;
-    const long long nunits = (long long)(a.nb - 1) * nseg;       // band 0 needs no map: the walker of band 0 ends the path itself
+    if (a.phase == 1 && __ldcg(a.miss) == 0) return;              // the corridor pass found the whole path
+    const bool corr = a.corr_w > 0 && a.phase == 0;
+    const int per_band = corr ? a.corr_w : nseg;
+    const long long nunits = (long long)(a.nb - 1) * per_band;   // band 0 needs no map: the walker of band 0 ends the path itself
     for (long long u = (long long)blockIdx.x * WARPS + w; u < nunits; u += nwarps) {
-        const int b = 1 + (int)(u / nseg), seg = (int)(u % nseg);
+        const int b = 1 + (int)(u / per_band);
+        int seg = (int)(u % per_band);
+        if (corr) {
+            int lo, hi;
+            corridor_range(a, b, By, LAG, lo, hi);
+            seg += lo;
+            if (seg > hi) continue;
+        }
         const int lc0 = seg * a.snap_chunks;
         int lc1 = lc0 + a.snap_chunks;
         if (seg == nseg - 1 || lc1 > nlc) lc1 = nlc;
@@ -163,6 +198,8 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
     __shared__ int wbase[kHopAhead];
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
+    if (a.phase == 1 && __ldcg(a.miss) == 0) return;          // the corridor pass found the whole path
+    const bool corr = a.corr_w > 0 && a.phase == 0;
     const int nunits = a.map_half ? 2 * a.nb : a.nb;         // unit u = map row u; the units of band 0 are never looked up
     const int first = a.map_half ? 2 : 1;
     const int wmax = ((a.m + 31) / 32) * 32 - kHopWin;       // last window start that stays inside a map row
@@ -212,14 +249,25 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
                 issue(2 * b - kHopAhead, jn, 2 * b - 1);
             } else {
                 if (j > 0) {
-                    jn = lookup(b, j - 1);
-                    // a negative label: the path left the segment that computed it through its left cut -- follow the cut cell's
-                    // label in the segment(s) to the left until it is a top-row column (a dependent load each)
                     int sg = ((j - 1) + cut_lag) / (32 * a.snap_chunks);
                     if (sg > a.nseg - 1) sg = a.nseg - 1;
-                    while (jn < 0 && sg > 0) {
-                        sg--;
-                        jn = __ldcg(a.cut + ((long long)b * a.nseg + sg) * 32 * cut_slots + (-jn - 1));
+                    int lo = 0, hi = a.nseg - 1;
+                    if (corr) corridor_range(a, b, By, cut_lag, lo, hi);
+                    bool out = sg < lo || sg > hi;                      // the path is outside the corridor: the full pass takes over
+                    if (!out) {
+                        jn = lookup(b, j - 1);
+                        // a negative label: the path left the segment that computed it through its left cut -- follow the cut cell's
+                        // label in the segment(s) to the left until it is a top-row column (a dependent load each)
+                        while (jn < 0 && sg > 0) {
+                            sg--;
+                            if (sg < lo) { out = true; break; }
+                            jn = __ldcg(a.cut + ((long long)b * a.nseg + sg) * 32 * cut_slots + (-jn - 1));
+                        }
+                    }
+                    if (out) {
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        if (lane == 0) *a.miss = 1;
+                        return;
                     }
                     if (jn < 0) jn = 0;               // cannot happen (segment 0 has no cut)
                 }
@@ -231,7 +279,7 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
         j = jn;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    if (lane == 0) a.off[a.nb] = off;
+    if (lane == 0) { a.off[a.nb] = off; if (a.phase == 0) *a.miss = 0; }      // (the full pass leaves the flag set: nwb200_trace_info reports it)
 }
 
 // ---------------------------------------------------------------------------------------------- pass C

@@ -198,6 +198,40 @@ def test_score_hash_multi_band_and_variants(engine, scoring, oracle):
         assert engine.score_hash() == exp.score_hash
 
 
+@pytest.mark.parametrize("kind", ["mutated", "long_indel", "random"])
+def test_corridor_maps_hit_miss_and_off(scoring, oracle, monkeypatch, kind):
+    """Origin maps restricted to a corridor around the line to the origin (long pairs): a path inside the corridor is found by the
+    corridor pass alone, a path that leaves it (a 2 500-letter deletion in the middle) sets the miss flag and the full pass that is
+    enqueued behind takes over; same transcript either way, and with the corridor switched off."""
+    from gpuseqalign_b200 import Engine, synth
+    subst = scoring["subst"]["blosum62"]
+    n = 40000                                  # (313 bands: more than the fill launch can host map units for, so pass A is the separate kernel)
+    x = synth.letters(611, n)
+    if kind == "mutated":
+        y = synth.mutated_copy(x, 612, n)
+    elif kind == "long_indel":
+        y = np.concatenate([x[:19000], x[21500:], synth.letters(613, 2500)])      # the path runs 2 500 columns off the line in the middle
+    else:
+        y = synth.letters(614, n)
+    exp = oracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True)
+    seen = {}
+    for d in ("512", "0", None):
+        if d is None: monkeypatch.delenv("NWB200_CORRIDOR", raising=False)
+        else: monkeypatch.setenv("NWB200_CORRIDOR", d)
+        eng = Engine(0)
+        try:
+            eng.set_scoring(subst, -11)
+            assert eng.align(y, x, keep_headers=True) == exp.score
+            assert eng.trace() == (exp.edit, exp.trace_hash), (kind, d)
+            seen[d] = eng.trace_info()
+        finally:
+            eng.close()
+    assert seen["512"]["corridor_segments"] > 0 and seen["512"]["corridor_segments"] * 2 <= seen["512"]["segments"]
+    assert seen["512"]["corridor_missed"] == (kind == "long_indel")
+    assert seen["0"]["corridor_segments"] == 0 and not seen["0"]["corridor_missed"]
+    assert not seen[None]["corridor_missed"] or kind == "long_indel"
+
+
 def _path_cells(edit: str, n: int, m: int):
     """Cells of the path described by a run-length transcript, top-left -> bottom-right."""
     import re
