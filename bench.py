@@ -38,7 +38,7 @@ if ROOT not in sys.path:
 SM_COUNT = 148
 DPX_PER_CLK_PER_SM = 64.0          # measured VIMNMX3 rate (profiles/microbench_r1.jsonl): 63.96 thread-ops/clk/SM
 MIX_CELLS_PER_CLK_PER_SM = 48.3    # measured IDP.4A + VIMNMX3 pair rate (same file): cells/clk/SM of the 2-instruction cell
-MIX16_CELLS_PER_CLK_PER_SM = 54.2  # measured IDP.4A + IDP.2A + VIMNMX3.U16x2 rate (profiles/microbench_r1z.jsonl)
+MIX16_CELLS_PER_CLK_PER_SM = 58.7  # measured rate of the packed cell mix, 0.5 PRMT + IDP.2A + VIMNMX3.U16x2 per two cells, 16 warps/SM (profiles/r2r_microbench_merge_variants.jsonl)
 ISSUE_PER_CLK_PER_SM = 128.0       # 4 schedulers x 32 lanes: the hard ceiling of thread-instructions per clock
 
 WORKLOADS = ("batch256", "pair16k", "wave200k", "scan4m")
@@ -553,6 +553,7 @@ def wl_wave(cx: Ctx, steps, warmup, main):
         score = eng.fetch_score()
         edit, th = eng.fetch_trace(1 << 20) if with_trace else ("", 0)
         lap = eng.timing()
+        tinfo = eng.trace_info() if with_trace else None      # corridor maps: segments computed per band, and whether the path left the corridor
         if gold:
             parity = {"score_matches_oracle": score == gold["score"]}
             if with_trace:
@@ -571,7 +572,7 @@ def wl_wave(cx: Ctx, steps, warmup, main):
         return {"value": cells * steps / ms_rank / 1e6, "ms_per_step": ms_rank / steps, "cells_job": cells, "cells_rank": cells,
                 "kernel_ms": lap.get("align_calc", 0.0), "kernel": "nw_fill_kernel", "launches": launches, "clocks": clocks,
                 "config": wave_config(n, 1), "scaling": "strong",
-                "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()},
+                "laps_ms_last_step": {k: round(v, 4) for k, v in lap.items()}, "traceback": tinfo,
                 "e2e": {"value": cells * e2e_steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * n), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_s / e2e_steps * 1e3},
                 "parity": parity, "dtype": "int32"}
@@ -683,7 +684,7 @@ def compact(r):
     """A workload's result as a secondary block."""
     if r is None:
         return None
-    keep = ("value", "ms_per_step", "kernel", "kernel_ms", "launches", "scaling", "laps_ms_last_step", "latency_floor", "parity", "wall_ms_per_step")
+    keep = ("value", "ms_per_step", "kernel", "kernel_ms", "launches", "scaling", "laps_ms_last_step", "traceback", "latency_floor", "parity", "wall_ms_per_step")
     out = {k: r[k] for k in keep if k in r and r[k] is not None}
     out["unit"] = "GCUPS"
     out["workload"] = r["config"]["workload"]
@@ -753,14 +754,14 @@ def main():
                          "peak_mix_measured": SM_COUNT * MIX_CELLS_PER_CLK_PER_SM * f_ghz,
                          "peak_issue_slots": SM_COUNT * ISSUE_PER_CLK_PER_SM * f_ghz,
                          "rank": "rank 0's kernel time and cells" if cx.world > 1 else "the one GPU"}}
-    if "batch2" in str(res["kernel"]):
+    if "batch2" in str(res["kernel"]) or "batch3" in str(res["kernel"]):
         # the packed kernel computes TWO cells per VIMNMX3.U16x2: against a roofline of one DPX op per two cells the same rate is half
         # the fraction; both are reported, together with the measured rate of the kernel's own instruction mix
         line["roofline"]["peak_packed16"] = 2.0 * peak
         line["roofline"]["frac_packed16"] = achieved / (2.0 * peak)
         line["roofline"]["peak_mix_measured"] = SM_COUNT * MIX16_CELLS_PER_CLK_PER_SM * f_ghz
         line["roofline"]["frac_of_mix_measured"] = achieved / (SM_COUNT * MIX16_CELLS_PER_CLK_PER_SM * f_ghz)
-    for k in ("laps_ms_last_step", "latency_floor", "wall_ms_per_step"):
+    for k in ("laps_ms_last_step", "traceback", "latency_floor", "wall_ms_per_step"):
         if res.get(k) is not None:
             line["roofline"][k] = res[k]
     if res.get("parity") is not None:
