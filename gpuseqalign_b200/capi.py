@@ -92,7 +92,8 @@ EXPORTS = [
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
     "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
-    "nwb200_trace_info", "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
+    "nwb200_trace_info", "nwb200_wave_keep_headers", "nwb200_wave_export_headers", "nwb200_wave_connect_headers", "nwb200_wave_gather_headers",
+    "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
 ]
 
 _lib = None
@@ -145,6 +146,10 @@ def load_library():
     L.nwb200_trace_values.argtypes = [vp, vp, C.c_size_t, P(C.c_size_t)]
     L.nwb200_get_memory_usage.argtypes = [vp, P(_MemUsage)]
     L.nwb200_trace_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.nwb200_wave_keep_headers.argtypes = [vp, C.c_int]
+    L.nwb200_wave_export_headers.argtypes = [vp, vp, vp]
+    L.nwb200_wave_connect_headers.argtypes = [vp, vp, vp]
+    L.nwb200_wave_gather_headers.argtypes = [vp, C.c_int]
     L.nwb200_wave_upload.argtypes = [vp, vp, i64, vp, i64, P(_Params), C.c_int, C.c_int, C.c_int]
     L.nwb200_wave_export.argtypes = [vp, vp]
     L.nwb200_wave_connect.argtypes = [vp, vp]
@@ -374,6 +379,25 @@ class Engine:
         has = C.c_int(0); s = C.c_int32(0)
         self._check(self._L.nwb200_wave_fetch(self._h, C.byref(has), C.byref(s)))
         return (s.value if has.value else None)
+
+    def wave_keep_headers(self, on: bool = True):
+        """Before wave_upload (world > 1): keep header rows and snapshots in the layout of the whole matrix, for a traceback."""
+        self._check(self._L.nwb200_wave_keep_headers(self._h, 1 if on else 0))
+
+    def wave_export_headers(self):
+        """(64-byte IPC handle of the header rows, of the snapshots) of this rank."""
+        hr = C.create_string_buffer(64); sn = C.create_string_buffer(64)
+        self._check(self._L.nwb200_wave_export_headers(self._h, hr, sn))
+        return hr.raw, sn.raw
+
+    def wave_connect_headers(self, hr_handles, snap_handles):
+        """Maps every other rank's header rows and snapshots (lists of 64-byte handles in rank order)."""
+        a = C.create_string_buffer(b"".join(hr_handles), 64 * len(hr_handles))
+        b = C.create_string_buffer(b"".join(snap_handles), 64 * len(snap_handles))
+        self._check(self._L.nwb200_wave_connect_headers(self._h, a, b))
+
+    def wave_gather_headers(self, full: bool = False):
+        self._check(self._L.nwb200_wave_gather_headers(self._h, 1 if full else 0))
 
     def scan_upload(self, y, x, rank: int, world: int) -> bytes:
         y = np.ascontiguousarray(y, dtype=np.uint8); x = np.ascontiguousarray(x, dtype=np.uint8)

@@ -117,6 +117,11 @@ struct nwb200_ctx {
     int wave_rank = 0, wave_world = 1, wave_wc = 0, wave_nq = 0, wave_nblocks = 0;
     long long wave_ldr = 0, wave_hr_stride = 0, wave_recv_stride = 0;
     bool wave_ready = false, wave_connected = false, wave_filled = false;
+    // traceback after a cross-GPU fill: header rows and snapshots in the layout of the whole matrix on every rank (its own column blocks
+    // filled in), the other ranks' buffers mapped on the rank that walks the path
+    bool wave_keep = false, wave_global = false;
+    void* wave_peer_hr[16] = {};
+    void* wave_peer_snap[16] = {};
     // row-parallel prefix-max scorer
     int scan_total = 0, scan_chunk0 = 0, scan_nchunks = 0, scan_per = 0;
     unsigned scan_epoch = 0;

@@ -318,7 +318,9 @@ __device__ __forceinline__ void fill_unit(const FillArgs& a, unsigned char* warp
     const unsigned pm = (lane >= SHM) ? 4u * (unsigned)(lane - SHM) : 128u + 4u * (unsigned)(32 - SHM + lane);
     constexpr int LCF = (HB0 + 3) / 32;                    // the first quad the warp below reads (columns -L4 ..) is the last quad of chunk LCF
     int cons_seen = 0;
-    int snap_left = a.snap_chunks, snap_k = 0;
+    // (a column block of the cross-GPU wavefront that keeps snapshots starts at a multiple of the snapshot spacing: its snapshots carry
+    //  the indices they have in the whole matrix)
+    int snap_left = a.snap_chunks, snap_k = (int)(c0 / (32LL * a.snap_chunks));
     int lc = 0;
     for (int left = nlc; left > 0; left--, lc++) {        // (a running count: written as lc < nlc, ptxas recomputes nlc from m every iteration)
         // ---- issue the prefetches of chunk lc + PD

@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
 #pragma unroll
             for (int r = 0; r < R; r++) { st.h[r] = sp[r]; st.o[r] = id0 - r; }
             st.dprev = sp[R];
-            st.up_next = sp[R + 1];
+            // lane 0's next input from above is the top row at the segment's first column: taken from the header row, not from the
+            // snapshot (the snapshot at the END of a column block of the cross-GPU fill saw a zero there: that column belongs to the
+            // next block, whose owner holds its header-row element)
+            st.up_next = (lane == 0) ? sm.rin[(32 * lc0) & (VR - 1)] : sp[R + 1];
             // lane 0's upper neighbours are cells of the band's top row: their label is their own column
             st.oprev = (lane == 0) ? 32 * lc0 : id0 - R;
             st.oup_next = (lane == 0) ? 32 * lc0 + 1 : id0 - (R + 1);
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
                         return;
                     }
                     if (jn < 0) jn = 0;               // cannot happen (segment 0 has no cut)
+                    if (jn > j) jn = j;               // cannot happen with this pair's headers (the walkers' check then fails)
                 }
                 issue(b - kHopAhead, jn, b - 1);
             }
@@ -309,8 +313,14 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
     int j = a.entry[b];
     int row = By - 1;
     int cnt = 0;
+    if (j < 0 || j > m) {                         // a map entry that is no column (headers that are not this pair's): reported by the pack kernel
+        if (lane == 0) { a.cnt[b] = 0; a.exitj[b] = -1; }
+        return;
+    }
+    int guard = m / 32 + By + 16;                 // every pass below consumes at least one column or one row
 
     for (;;) {
+        if (--guard < 0) { j = -1; break; }
         if (j == 0) {                             // column 0: the path goes straight up (nwtrace1_plain.cpp:57-63 with j == 0)
             const int k = row - rmin + 1;
             for (int t = lane; t < k; t += 32) out[cnt + t] = 2;
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(32) nw_walk_kernel(const TraceArgs a, const in
 #pragma unroll
             for (int r = 0; r < R; r++) st.h[r] = sp[r];
             st.dprev = sp[R];
-            st.up_next = sp[R + 1];
+            st.up_next = (lane == 0) ? sm.rin[(32 * lc0) & (VR - 1)] : sp[R + 1];      // (see nw_map_kernel)
         } else {
 #pragma unroll
             for (int r = 0; r < R; r++) st.h[r] = 0;

@@ -45,6 +45,14 @@ int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
     return NWB200_SUCCESS;
 }
 
+// half width (columns) of the traceback's corridor around the line to the origin; 0: no corridor (nwb200_capi_trace.inc, nw_trace.cuh)
+long long trace_corridor_halfwidth(const Geometry& g)
+{
+    long long d = g.m / 32 > 4096 ? g.m / 32 : 4096;
+    if (const char* e = getenv("NWB200_CORRIDOR")) d = atoll(e);
+    return d > 0 ? d : 0;
+}
+
 template <int R, int K, int W>
 int launch_fill_t(nwb200_ctx* c, const FillArgs& a, int grid, int cluster)
 {
@@ -171,6 +179,10 @@ void nwb200_destroy(nwb200_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->wave_peer_base) { cudaIpcCloseMemHandle(c->wave_peer_base); c->wave_peer_base = nullptr; }
+    for (int r = 0; r < 16; r++) {
+        if (c->wave_peer_hr[r]) cudaIpcCloseMemHandle(c->wave_peer_hr[r]);
+        if (c->wave_peer_snap[r]) cudaIpcCloseMemHandle(c->wave_peer_snap[r]);
+    }
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync, &c->d_order,
                       &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
                       &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})

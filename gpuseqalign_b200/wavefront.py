@@ -51,6 +51,46 @@ def wave_align(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: in
     return int(t.item())
 
 
+def wave_trace_setup(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: int = 1, block_cols: int = 2048, tracer: int = 0,
+                     params=None, group=None):
+    """wave_setup for a fill that is followed by a traceback on rank `tracer` (world > 1): every rank keeps the header rows and
+    snapshots of its column blocks, the tracer maps them all.  block_cols must be a multiple of the snapshot spacing (512 columns for
+    pairs longer than 65 536, 256 below, or params.tile_cols)."""
+    import torch.distributed as dist
+    engine.wave_keep_headers(True)
+    try:
+        handle = engine.wave_upload(y, x, rank, world, block_cols, params)
+    finally:
+        engine.wave_keep_headers(False)
+    hs = engine.wave_export_headers()
+    _connect(engine, handle, rank, world, group)
+    handles: list = [None] * world
+    dist.all_gather_object(handles, hs, group=group)
+    if rank == tracer:
+        engine.wave_connect_headers([h[0] for h in handles], [h[1] for h in handles])
+    dist.barrier(group=group)
+
+
+def wave_trace(engine, *, rank: int = 0, world: int = 1, tracer: int = 0, cap: int = 0, group=None):
+    """After wave_fill + wave_fetch on every rank: rank `tracer` pulls the headers the traceback's corridor can touch over NVLink, runs
+    the traceback and -- when the path left the corridor -- repeats it on all headers.  Returns (transcript, trace hash, info) on the
+    tracer, None elsewhere.  Collective: contains the barrier that separates the fills from the peer copies."""
+    import torch.distributed as dist
+    dist.barrier(group=group)                      # every rank has synchronised its fill (wave_fetch does)
+    out = None
+    if rank == tracer:
+        engine.wave_gather_headers(False)
+        engine.trace_resident()
+        info = engine.trace_info()
+        if info["corridor_missed"]:
+            engine.wave_gather_headers(True)
+            engine.trace_resident()
+        edit, th = engine.fetch_trace(cap) if cap else engine.fetch_trace()
+        out = (edit, th, info)
+    dist.barrier(group=group)                      # nobody starts the next fill (and overwrites its headers) while the tracer still reads them
+    return out
+
+
 def scan_align(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, world: int = 1, epoch: int = 1, group=None) -> int:
     """Score of NW(y, x) for a matrix with few rows and very many columns (row-parallel prefix max, csrc/nw_scan.cuh);
     the chunks of 4096 columns are dealt to the ranks in contiguous ranges.  Same calling convention as wave_align."""

@@ -206,6 +206,20 @@ NWB200_API int  nwb200_wave_connect(nwb200_ctx* ctx, const void* right_peer_hand
 NWB200_API int  nwb200_wave_fill(nwb200_ctx* ctx, unsigned epoch);           /* async on the ctx stream */
 NWB200_API int  nwb200_wave_fetch(nwb200_ctx* ctx, int* has_score, int32_t* align_cost);   /* syncs */
 
+/* Traceback of a cross-GPU fill (BASELINE config 5 at N > 1; the reference's semantics: nwtrace2_sparse.cpp:102-257 on the header
+ * matrices of the whole pair).  Every rank keeps the header rows and snapshots of its own column blocks in the layout of the whole
+ * matrix; the rank that walks the path pulls the other ranks' parts over NVLink (peer copies from buffers mapped with CUDA IPC; only
+ * the bands of a block that the traceback's corridor can touch unless `full`) and then runs the ordinary traceback:
+ *   every rank:  nwb200_wave_keep_headers(1) -> nwb200_wave_upload (block_cols a multiple of tile_cols) -> nwb200_wave_export +
+ *                nwb200_wave_export_headers -> [exchange] -> nwb200_wave_connect -> (tracing rank: nwb200_wave_connect_headers)
+ *                -> [barrier] -> nwb200_wave_fill -> nwb200_wave_fetch -> [barrier: every fill is complete]
+ *   tracing rank: nwb200_wave_gather_headers(0) -> nwb200_trace_resident -> nwb200_trace_info; if the path left the corridor:
+ *                nwb200_wave_gather_headers(1) -> nwb200_trace_resident;  -> nwb200_fetch_trace. */
+NWB200_API int  nwb200_wave_keep_headers(nwb200_ctx* ctx, int on);
+NWB200_API int  nwb200_wave_export_headers(nwb200_ctx* ctx, void* hr_handle64, void* snap_handle64);
+NWB200_API int  nwb200_wave_connect_headers(nwb200_ctx* ctx, const void* hr_handles /* world x 64 B */, const void* snap_handles /* world x 64 B */);
+NWB200_API int  nwb200_wave_gather_headers(nwb200_ctx* ctx, int full);          /* async on the ctx stream */
+
 /* Few rows x very many columns (BASELINE config 4): the row-parallel prefix-max scorer, one warp per strip of 512
  * columns (groups of 16 strips dealt to the ranks), one int per row crossing each strip (and GPU) boundary.  Score only.  Multi-GPU use follows the wavefront
  * protocol: nwb200_scan_upload -> nwb200_wave_export -> nwb200_wave_connect -> [barrier] -> nwb200_scan_fill -> nwb200_scan_fetch. */

@@ -4,6 +4,7 @@ the reference's own gpu9 / own benchmark executable on the box.
 The multi-rank tests skip with a reason on a one-GPU lease (the same protocols run there with world = 1 in
 test_gpu_fill.py / test_gpu_big.py); on a multi-GPU lease they spawn 2 ranks (4 when the box has them):
   * column-block wavefront (wave_align): a 3 000 x 20 000 pair against the oracle, cfg5 (200 000^2) against its golden score;
+  * cross-GPU fill + traceback from gathered headers (wave_trace): 40 000^2 pairs against the oracle, cfg5 against its golden transcript;
   * prefix-max scorer (scan_align): small shapes against the oracle, cfg4 (2 048 x 4 194 304) against its golden score;
   * sharded align_batch: every rank aligns its shard on ITS GPU, the gathered score vector against the oracle;
   * the strong-scaling shards of the full cfg3 job: per-eighth sha-256 of the scores against tests/golden/batch_golden.json.
@@ -41,7 +42,9 @@ def _worker(rank, world, port, what, q):
     from gpuseqalign_b200.sharding import partition_pairs, shard_batch, gather_scores
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+    # (a short collective timeout: a rank that fails must not leave the others waiting in a barrier for ten minutes)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank), timeout=datetime.timedelta(seconds=120))
     out = {}
     try:
         with open(os.path.join(ROOT, "tests", "golden", "scoring.json")) as f:
@@ -65,6 +68,43 @@ def _worker(rank, world, port, what, q):
             x = synth.letters(5001, 200000); y = synth.letters(5004, 200000)
             epoch += 1
             out["cfg5"] = (wave_align(eng, y, x, rank=rank, world=world, block_cols=2048, epoch=epoch), big["cfg5_random"]["score"])
+        elif what == "wavetrace":
+            # cross-GPU fill + traceback on rank 0 from the gathered headers (nwb200_wave_gather_headers): transcript and trace hash
+            # against the oracle (moderate pairs: path inside the corridor, and a long indel that leaves it) and cfg5 against its golden
+            from oracle import pyoracle
+            from gpuseqalign_b200.wavefront import wave_trace_setup, wave_trace
+            n = 40000
+            x = synth.letters(611, n)
+            cases = {"mutated": synth.mutated_copy(x, 612, n), "random": synth.letters(614, n),
+                     "long_indel": np.concatenate([x[:19000], x[21500:], synth.letters(613, 2500)])}
+            os.environ["NWB200_CORRIDOR"] = "512"
+            for name, y in cases.items():
+                exp = pyoracle.align_pair(y, x, subst, -11, want_hash=False, want_trace=True) if rank == 0 else None
+                for block in (5120, 20480):
+                    epoch += 1
+                    wave_trace_setup(eng, y, x, rank=rank, world=world, block_cols=block)
+                    eng.wave_fill(epoch)
+                    score = eng.wave_fetch()
+                    if os.environ.get("NWB200_TEST_VERBOSE"): print(f"rank {rank}: {name} block {block}: filled, score {score}", file=sys.stderr, flush=True)
+                    tr = wave_trace(eng, rank=rank, world=world)
+                    if os.environ.get("NWB200_TEST_VERBOSE"): print(f"rank {rank}: {name} block {block}: traced {tr[2] if tr else None}", file=sys.stderr, flush=True)
+                    if rank == 0:
+                        out[f"{name}_block{block}_trace"] = ((tr[0], tr[1]), (exp.edit, exp.trace_hash))
+                        out[f"{name}_block{block}_missed"] = (tr[2]["corridor_missed"], name == "long_indel")
+                    if score is not None:
+                        out[f"{name}_block{block}_score"] = (score, int(pyoracle.fill_rolling(y, x, subst, -11)[0]))
+            del os.environ["NWB200_CORRIDOR"]
+            x = synth.letters(5001, 200000); y = synth.letters(5004, 200000)
+            epoch += 1
+            wave_trace_setup(eng, y, x, rank=rank, world=world, block_cols=(200000 // world + 511) // 512 * 512)
+            eng.wave_fill(epoch)
+            score = eng.wave_fetch()
+            tr = wave_trace(eng, rank=rank, world=world, cap=1 << 20)
+            g5 = big["cfg5_random"]
+            if score is not None:
+                out["cfg5_score"] = (score, g5["score"])
+            if rank == 0:
+                out["cfg5_trace"] = ((f"{tr[1]:08x}", hashlib.sha256(tr[0].encode()).hexdigest()), (g5["trace_hash"], g5["edit_sha256"]))
         elif what == "scan":
             from oracle import pyoracle
             for n, m, sy, sx in ((37, 9000, 71, 72), (300, 70000, 73, 74), (1, 5000, 75, 76)):
@@ -103,12 +143,14 @@ def _worker(rank, world, port, what, q):
         eng.close()
         q.put((rank, out, None))
     except Exception as ex:          # reported to the parent, which fails the test
-        q.put((rank, out, f"{type(ex).__name__}: {ex}"))
+        import traceback
+        q.put((rank, out, f"{type(ex).__name__}: {ex}\n{traceback.format_exc()}"))
+        os._exit(1)                   # (no orderly shutdown: the other ranks may be waiting in a collective this rank will never join)
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, what, timeout=600):
+def _run(world, what, timeout=300):
     import torch.multiprocessing as mp
     port = _free_port()
     ctx = mp.get_context("spawn")
@@ -116,13 +158,26 @@ def _run(world, what, timeout=600):
     procs = [ctx.Process(target=_worker, args=(r, world, port, what, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=timeout) for _ in procs]
+    import queue as _queue
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=timeout))
+            if res[-1][2] is not None:
+                break                                   # a rank failed: the others cannot finish their collectives
+    except _queue.Empty:
+        pass
+    failed = len(res) < len(procs) or any(r[2] is not None for r in res)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=5 if failed else 120)
+        if p.is_alive():
+            p.kill()
+    assert res, f"{what}: no rank reported within {timeout} s"
     for rank, out, err in res:
         assert err is None, f"rank {rank}: {err}"
         for k, (got, exp) in out.items():
             assert got == exp, f"rank {rank} {what}/{k}: {got} != {exp}"
+    assert len(res) == len(procs), f"{what}: only ranks {[r[0] for r in res]} reported"
     assert all(p.exitcode == 0 for p in procs)
     return res
 
@@ -132,7 +187,7 @@ def _worlds():
     return [w for w in (2, 4) if w <= n]
 
 
-@pytest.mark.parametrize("what", ["wave", "scan", "batch"])
+@pytest.mark.parametrize("what", ["wave", "wavetrace", "scan", "batch"])
 def test_multi_gpu_paths_bit_exact(what, oracle):
     worlds = _worlds()
     if not worlds:
