@@ -125,7 +125,7 @@ def pair_config(n, m, with_trace=True):
 
 def wave_config(n, world):
     how = "one GPU: fill + sparse traceback recompute" if world == 1 else \
-        f"column-block wavefront over {world} GPUs, border columns as peer stores over NVLink; score only (traceback of a distributed fill: see DESIGN.md)"
+        f"column-block wavefront over {world} GPUs, border columns as peer stores over NVLink; fill on every GPU + traceback on rank 0 from the headers it pulls over NVLink"
     return {"workload": f"cfg5: single long pair {n}x{n}, {how}", "seeds": "X 5001, Y 5004 (splitmix64, independent)",
             "subst": "blosum62", "gap": -11, "l2": "flushed between timed steps (256 MiB memset)"}
 
@@ -576,31 +576,73 @@ def wl_wave(cx: Ctx, steps, warmup, main):
                 "e2e": {"value": cells * e2e_steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * n), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_s / e2e_steps * 1e3},
                 "parity": parity, "dtype": "int32"}
-    block = args.wave_block if args.wave_block > 0 else max(2048, ((n + cx.world - 1) // cx.world + 31) // 32 * 32)
-    wave_setup(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block)
+    with_trace = not args.no_trace
+    per_rank = (n + cx.world - 1) // cx.world
+    block = args.wave_block if args.wave_block > 0 else max(2048, (per_rank + 511) // 512 * 512)     # (a multiple of the snapshot spacing: the traceback needs it)
+    if with_trace:
+        from gpuseqalign_b200.wavefront import wave_trace_setup, wave_trace
+        wave_trace_setup(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block)
+    else:
+        wave_setup(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block)
     sampler = ClockSampler(cx.local) if main else None
     if sampler:
         sampler.__enter__()
-    dev_ms, wall_s, score, launches = _collective_steps(cx, eng.wave_fill, eng.wave_fetch, steps, warmup)
+    # every step: one cooperative fill launch per rank with a fresh epoch (device time = max over ranks of the launch), then -- with the
+    # traceback -- the pull of the headers and the traceback on rank 0 (wall time between the barriers that bracket it, max over ranks)
+    trace_state = {"walls": [], "last": None}
+
+    def fetch():
+        s_ = eng.wave_fetch()
+        if with_trace:
+            t0 = time.perf_counter()
+            tr = wave_trace(eng, rank=cx.rank, world=cx.world, cap=1 << 21)
+            trace_state["walls"].append(time.perf_counter() - t0)
+            if tr is not None:
+                trace_state["last"] = tr
+        return s_
+
+    dev_ms, wall_s, score, launches = _collective_steps(cx, eng.wave_fill, fetch, steps, warmup)
     if sampler:
         sampler.__exit__()
     score = int(cx.reduce(float(score) if score is not None else -2.0 ** 62))
+    trace_ms = 0.0
+    tinfo = None
+    if with_trace:
+        timed = trace_state["walls"][-steps:]                  # (the warm-up steps carry the first peer mapping)
+        trace_ms = cx.reduce(sum(timed) / max(1, len(timed)) * 1e3)
     if gold:
         parity = {"score_matches_oracle": score == gold["score"]}
-    # end to end: the whole public call (upload on every rank, handle exchange, fill, score)
+        if with_trace and cx.rank == 0 and trace_state["last"] is not None:
+            edit, th, tinfo = trace_state["last"]
+            parity["trace_hash_matches_oracle"] = f"{th:08x}" == gold["trace_hash"]
+            parity["edit_sha256_matches_oracle"] = hashlib.sha256(edit.encode()).hexdigest() == gold["edit_sha256"]
+    # end to end: the whole public call (upload on every rank, handle exchange, fill, score, traceback)
     e2e_steps = max(1, min(steps, 3))
     cx.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         cx.epoch += 1
-        wave_align(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block, epoch=cx.epoch)
+        if with_trace:
+            wave_trace_setup(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block)
+            eng.wave_fill(cx.epoch)
+            eng.wave_fetch()
+            wave_trace(eng, rank=cx.rank, world=cx.world, cap=1 << 21)
+        else:
+            wave_align(eng, y, x, rank=cx.rank, world=cx.world, block_cols=block, epoch=cx.epoch)
     cx.barrier()
     e2e_s = cx.reduce(time.perf_counter() - t0)
-    return {"value": cells * steps / dev_ms / 1e6, "ms_per_step": dev_ms / steps, "cells_job": cells, "cells_rank": cells / cx.world,
+    # with the traceback a step is what the wall clock sees between the barrier in front of the fills and the end of the traceback (max over
+    # ranks): rank 0's wait for the last rank's fill is inside `gather_and_trace_wall_rank0`, so the laps do not add up
+    step_ms = wall_s / steps * 1e3 if with_trace else dev_ms / steps
+    trace_dev_ms = cx.reduce(eng.timing().get("trace_calc", 0.0) if (with_trace and cx.rank == 0) else 0.0)
+    return {"value": cells / step_ms / 1e6, "ms_per_step": step_ms, "cells_job": cells, "cells_rank": cells / cx.world,
             "kernel_ms": dev_ms / steps, "kernel": "nw_fill_kernel (column-block wavefront)", "launches": launches,
             "clocks": sampler.summary() if sampler else None, "config": dict(wave_config(n, cx.world), block_cols=block), "scaling": "strong",
             "wall_ms_per_step": wall_s / steps * 1e3,
-            "e2e": {"value": cells * e2e_steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * n * cx.world), "d2h_bytes_per_step": 4,
+            "laps_ms_last_step": {"align_calc_max_over_ranks": round(dev_ms / steps, 4), "trace_calc_rank0": round(trace_dev_ms, 4),
+                                  "gather_and_trace_wall_rank0": round(trace_ms, 4)},
+            "traceback": tinfo,
+            "e2e": {"value": cells * e2e_steps / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(2 * n * cx.world), "d2h_bytes_per_step": 4 + (n * 2 // 3 if with_trace else 0),
                     "ms_per_step": e2e_s / e2e_steps * 1e3},
             "parity": parity, "dtype": "int32"}
 

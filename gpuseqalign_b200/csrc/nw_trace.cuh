@@ -450,6 +450,63 @@ __global__ void __launch_bounds__(1024) nw_pack_kernel(const TraceArgs a)
 }
 
 
+// ---------------------------------------------------------------------------------------------- headers of a cross-GPU fill
+// The rank that walks the path pulls what the traceback reads from the other ranks' buffers (mapped with CUDA IPC, loads over NVLink):
+// for band b the header row above it and its snapshots, in the columns of the traceback's corridor (+ slack for the windows of the
+// map segments and walkers) -- or in all columns (`full`: after a corridor miss).  Column c of every row lives on rank
+// (c / wc) % world; rows and snapshots have the layout of the whole matrix on every rank.  One CTA per band.
+struct GatherArgs {
+    unsigned long long* HR;                  // this rank's header rows
+    int* snap;                               // this rank's snapshots
+    const unsigned long long* peer_HR[16];   // the other ranks' (nullptr: this rank)
+    const int* peer_snap[16];
+    int rank, world;
+    long long wc;                            // columns per block
+    int n, m, nb, pad, By, Bx;
+    long long ldr;
+    int nsnap, snap_ints;                    // snapshots per band, ints per snapshot (32 lanes x SNAP_INTS)
+    long long d, slack;                      // corridor half width (0: everything), slack on either side
+    int full;
+};
+
+__global__ void __launch_bounds__(256) nw_gather_kernel(const GatherArgs a)
+{
+    const int b = blockIdx.x;                // 0 .. nb-1: the band whose top row (b >= 1) and snapshots are pulled; nb: the score element's row
+    if (b > a.nb) return;
+    long long c_lo = 0, c_hi = a.m;          // columns [c_lo, c_hi)
+    if (b == a.nb) { c_lo = a.m - 1; c_hi = a.m; }
+    else if (!a.full && a.d > 0) {
+        long long rb = (long long)(b + 1) * a.By - a.pad, rt = (long long)b * a.By - a.pad;
+        if (rb > a.n) rb = a.n;
+        if (rt < 0) rt = 0;
+        c_lo = (long long)a.m * rt / a.n - a.d - a.slack;
+        c_hi = (long long)a.m * rb / a.n + a.d + a.slack;
+        if (c_lo < 0) c_lo = 0;
+        if (c_hi > a.m) c_hi = a.m;
+    }
+    // ---- header row b
+    unsigned long long* dst = a.HR + (long long)b * a.ldr + kPadL;
+    for (long long c = c_lo + threadIdx.x; b >= 1 && c < c_hi; c += blockDim.x) {
+        const int owner = (int)((c / a.wc) % a.world);
+        const unsigned long long* src = a.peer_HR[owner];
+        if (src != nullptr) dst[c] = src[(long long)b * a.ldr + kPadL + c];
+    }
+    if (b == a.nb) return;
+    // ---- snapshots of band b whose boundary column (k + 1) * Bx lies in the range (snapshot k belongs to the block of column k * Bx)
+    long long k_lo = c_lo / a.Bx - 1, k_hi = c_hi / a.Bx + 1;
+    if (k_lo < 0) k_lo = 0;
+    if (k_hi > a.nsnap) k_hi = a.nsnap;
+    for (long long k = k_lo; k < k_hi; k++) {
+        const int owner = (int)(((k * a.Bx) / a.wc) % a.world);
+        const int* src = a.peer_snap[owner];
+        if (src == nullptr) continue;
+        const long long off = ((long long)b * a.nsnap + k) * a.snap_ints;
+        const int4* s4 = reinterpret_cast<const int4*>(src + off);
+        int4* d4 = reinterpret_cast<int4*>(a.snap + off);
+        for (int i = threadIdx.x; i < a.snap_ints / 4; i += blockDim.x) d4[i] = s4[i];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- score matrix slabs
 // Re-sweeps bands b0 .. b0+nbands-1 from their header rows and writes EVERY cell (shifted value P) to a row-major
 // slab: slab[(b-b0)*By + local row][kPadL + c].  Used by the score hash (NwHash1_Plain / NwHash2_Sparse semantics,

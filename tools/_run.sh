@@ -2,6 +2,5 @@ run() { timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 rm -f gpurun_out/r2s_wavetrace.jsonl
 run 40000 random,mutated,long_indel 5120,2048
 NWB200_CORRIDOR=512 run 40000 random,long_indel 5120
-run 200000 random 100352,25088
-cat gpurun_out/r2s_wavetrace.jsonl | cut -c1-400
-python -m pytest tests/test_gpu_fill.py tests/test_gpu_big.py -m gpu -x -q 2>&1 | tail -2
+run 200000 random,random 100352,25088
+cat gpurun_out/r2s_wavetrace.jsonl | cut -c1-300
