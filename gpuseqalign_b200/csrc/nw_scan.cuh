@@ -27,16 +27,15 @@
 
 namespace nwb {
 
-constexpr int kScanWarps = 16;                          // warps (= strips) per CTA / group
-constexpr int kScanT = 32 * kScanWarps;                 // threads per CTA
+constexpr int kScanMaxWarps = 16;                       // warps (= strips) per CTA / group: 16, 8 or 4 (template parameter WARPS).  An SM holds 16 warps'
+                                                        // profiles either way; narrower groups are more CTAs per SM, whose per-row rounds overlap
 constexpr int kScanC = 16;                              // columns per lane
-constexpr int kScanStrip = 32 * kScanC;                 // columns per strip (one warp)
-constexpr int kScanW = kScanWarps * kScanStrip;         // columns per group (one CTA at a time): the unit the host deals to the ranks
+constexpr int kScanStrip = 32 * kScanC;                 // columns per strip (one warp); a group (the unit the host deals to the ranks) is WARPS strips
 constexpr int kScanAhead = 4;                           // rows the carry of the left group is requested ahead (global memory)
 constexpr int kScanLag = 6;                             // rows a group falls back behind its left neighbour when a request came back empty
 constexpr int kScanRing = 32;                           // rows of the shared-memory rings (strip maxima, group carry)
 __host__ __device__ constexpr size_t scan_warp_smem(int S) { return (size_t)(S + 1) * kScanStrip; }
-__host__ __device__ constexpr size_t scan_cta_smem(int S) { return (size_t)kScanWarps * scan_warp_smem(S) + (size_t)kScanRing * (kScanWarps + 1) * 8; }
+__host__ __device__ constexpr size_t scan_cta_smem(int S, int warps) { return (size_t)warps * scan_warp_smem(S) + (size_t)kScanRing * (warps + 1) * 8; }
 
 struct ScanArgs {
     const uint8_t* y;                 // n row letters
@@ -86,7 +85,7 @@ __device__ __forceinline__ void stg64_relaxed_if(bool p, unsigned long long* add
 
 // The row loop of one strip.  FROM_GLOBAL: this warp (warp 0 of a group that has a group to its left) fetches the group's carry
 // from global memory and publishes it in shared memory for the other warps.  HAS_GCIN: the group has a carry coming in at all.
-template <bool FROM_GLOBAL, bool HAS_GCIN>
+template <bool FROM_GLOBAL, bool HAS_GCIN, int WARPS>
 __device__ __forceinline__ void scan_rows(const ScanArgs& a, const int lane, const int w, const unsigned prof_lane_s, const unsigned tot_s, const unsigned gcin_s,
                                           const unsigned prog_s, const unsigned long long* __restrict__ cin_g, unsigned long long* cout_g,
                                           const bool to_global, int (&prev)[kScanC])
@@ -102,11 +101,11 @@ __device__ __forceinline__ void scan_rows(const ScanArgs& a, const int lane, con
     // what this lane gathers per row: the strip maximum of warp `lane` (lanes < w), the group's carry (lane 31), nothing (others)
     const bool gather = lane < w || (HAS_GCIN && lane == 31);
     const unsigned gather_s = (lane == 31 ? gcin_s : tot_s + 8u * (unsigned)lane);
-    const unsigned gather_step = (lane == 31 ? 8u : 8u * kScanWarps);           // bytes from one row's slot to the next
+    const unsigned gather_step = (lane == 31 ? 8u : 8u * WARPS);           // bytes from one row's slot to the next
     const unsigned mytot_s = tot_s + 8u * (unsigned)w;
-    const bool pub_tot = lane == 31, pub_out = to_global && lane == 31, pub_prog = w == kScanWarps - 1 && lane == 0;
+    const bool pub_tot = lane == 31, pub_out = to_global && lane == 31, pub_prog = w == WARPS - 1 && lane == 0;
     const unsigned at0 = gather ? gather_s : mytot_s;                           // lanes that gather nothing load their own warp's slot (and ignore it)
-    const unsigned step0 = gather ? gather_step : 8u * kScanWarps;
+    const unsigned step0 = gather ? gather_step : 8u * WARPS;
 
     for (int i = 1; i <= n; i++) {
         const unsigned slot = (unsigned)i & (kScanRing - 1);
@@ -161,7 +160,7 @@ __device__ __forceinline__ void scan_rows(const ScanArgs& a, const int lane, con
         int incl = run;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) incl = max(incl, __shfl_up_sync(kFull, incl, d));
-        sts64_if(pub_tot, mytot_s + 8u * kScanWarps * slot, ((unsigned long long)(unsigned)i << 32) | (unsigned)incl);
+        sts64_if(pub_tot, mytot_s + 8u * WARPS * slot, ((unsigned long long)(unsigned)i << 32) | (unsigned)incl);
         int excl = __shfl_up_sync(kFull, incl, 1);
         if (lane == 0) excl = 0;
         // ---- everything to the left of the strip: one load per lane, poll until the row tags match, one REDUX.MAX
@@ -186,7 +185,7 @@ __device__ __forceinline__ void scan_rows(const ScanArgs& a, const int lane, con
         // ---- progress / back-pressure, every 8 rows: nobody runs more than 16 + 7 rows ahead of the last warp (which waits for everybody)
         if ((i & 7) == 0) {
             sts32_if(pub_prog, prog_s, i);
-            if (w != kScanWarps - 1) {          // (warp-uniform)
+            if (w != WARPS - 1) {          // (warp-uniform)
                 unsigned polls = 0;
                 while (lds_volatile1(prog_s) < i - 16) { if (++polls > (1u << 24)) { atomicExch(a.err, 1); break; } }
             }
@@ -194,15 +193,17 @@ __device__ __forceinline__ void scan_rows(const ScanArgs& a, const int lane, con
     }
 }
 
-__global__ void __launch_bounds__(kScanT, 1) nw_scan_kernel(const ScanArgs a)
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, kScanMaxWarps / WARPS) nw_scan_kernel(const ScanArgs a)
 {
+    constexpr int kScanWarps = WARPS, kScanT = 32 * WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_prog;                        // rows the last warp has completed (multiples of 8)
     __shared__ int s_group;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int n = a.n, S = a.S;
     // prof[letter][column of the strip] bytes s'(letter, x[column]); row S is all zero
-    const unsigned prof_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)w * scan_warp_smem(S));
+    const unsigned prof_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)w * scan_warp_smem(S));      // (kScanWarps, kScanT: this instance's)
     const unsigned tot_s = (unsigned)__cvta_generic_to_shared(smem_raw + (size_t)kScanWarps * scan_warp_smem(S));      // [kScanRing][kScanWarps] (row | strip maximum)
     const unsigned gcin_s = tot_s + (unsigned)(kScanRing * kScanWarps * 8);                                            // [kScanRing] (row | carry into the group)
     const unsigned prog_s = (unsigned)__cvta_generic_to_shared(&s_prog);
@@ -251,9 +252,9 @@ __global__ void __launch_bounds__(kScanT, 1) nw_scan_kernel(const ScanArgs a)
 #pragma unroll
         for (int k = 0; k < kScanC; k++) prev[k] = 0;
         const unsigned prof_lane_s = prof_s + 16u * (unsigned)lane;
-        if (gg == 0) scan_rows<false, false>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
-        else if (w == 0) scan_rows<true, true>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
-        else scan_rows<false, true>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
+        if (gg == 0) scan_rows<false, false, WARPS>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
+        else if (w == 0) scan_rows<true, true, WARPS>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
+        else scan_rows<false, true, WARPS>(a, lane, w, prof_lane_s, tot_s, gcin_s, prog_s, cin_g, cout_g, to_global, prev);
         if (dbg) dbg[5] = globaltimer_ns();
         // ---- the score lives at column m of the last row
         if (a.m - 1 >= c0 && a.m - 1 < c0 + kScanC) {

@@ -1,6 +1,7 @@
-run() { timeout 100 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/wave_trace_check.py "$@" >> gpurun_out/r2s_wavetrace.jsonl 2> gpurun_out/r2s_wavetrace.err; echo "rc=$? ($*)"; grep -h "NwB200Error\|Error:" gpurun_out/r2s_wavetrace.err | head -3; }
-rm -f gpurun_out/r2s_wavetrace.jsonl
-run 40000 random,mutated,long_indel 5120,2048
-NWB200_CORRIDOR=512 run 40000 random,long_indel 5120
-run 200000 random,random 100352,25088
-cat gpurun_out/r2s_wavetrace.jsonl | cut -c1-300
+python -m pytest tests/test_gpu_big.py -m gpu -x -q -k "prefix or cfg4 or scan" 2>&1 | tail -3
+for w in 16 8 4; do
+NWB200_SCAN_WARPS=$w python bench.py --workload scan4m --steps 5 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/r2u_scan_w$w.json 2> gpurun_out/r2u_scan_w$w.err; echo rc=$?
+python -c "
+import json
+d=json.loads(open('gpurun_out/r2u_scan_w$w.json').read().strip().splitlines()[-1]); print($w, d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('parity'))"
+done
