@@ -92,7 +92,7 @@ EXPORTS = [
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
     "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
-    "nwb200_trace_info", "nwb200_wave_keep_headers", "nwb200_wave_export_headers", "nwb200_wave_connect_headers", "nwb200_wave_gather_headers",
+    "nwb200_batch_resident_variant", "nwb200_trace_info", "nwb200_wave_keep_headers", "nwb200_wave_export_headers", "nwb200_wave_connect_headers", "nwb200_wave_gather_headers",
     "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
 ]
 
@@ -146,6 +146,7 @@ def load_library():
     L.nwb200_trace_values.argtypes = [vp, vp, C.c_size_t, P(C.c_size_t)]
     L.nwb200_get_memory_usage.argtypes = [vp, P(_MemUsage)]
     L.nwb200_trace_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.nwb200_batch_resident_variant.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.nwb200_wave_keep_headers.argtypes = [vp, C.c_int]
     L.nwb200_wave_export_headers.argtypes = [vp, vp, vp]
     L.nwb200_wave_connect_headers.argtypes = [vp, vp, vp]
@@ -321,6 +322,17 @@ class Engine:
 
     def batch_resident(self):
         self._check(self._L.nwb200_batch_resident(self._h))
+
+    VARIANTS = {"nw_affine": 1, "sw_linear": 2, "sw_affine": 3}
+
+    def batch_resident_variant(self, variant: str, gap_open: int, gap_extend: int = 0):
+        """The resident batch under an affine-gap / local variant (include/nwb200.h: NWB200_VARIANT_*); fetch_batch_scores afterwards."""
+        self._check(self._L.nwb200_batch_resident_variant(self._h, self.VARIANTS[variant], gap_open, gap_extend))
+
+    def align_batch_variant(self, letters, offY, lenY, offX, lenX, variant: str, gap_open: int, gap_extend: int = 0) -> np.ndarray:
+        self.upload_batch(letters, offY, lenY, offX, lenX)
+        self.batch_resident_variant(variant, gap_open, gap_extend)
+        return self.fetch_batch_scores()
 
     def fetch_batch_scores(self) -> np.ndarray:
         out = np.empty(self._npairs, dtype=np.int32)

@@ -4,6 +4,7 @@
 #include "nw_batch.cuh"
 #include "nw_batch2.cuh"
 #include "nw_batch3.cuh"
+#include "nw_gotoh.cuh"
 
 namespace nwb {
 namespace {
@@ -206,6 +207,40 @@ int launch_batch_trace_t(nwb200_ctx* c, const BatchTraceArgs& a0, int need_chunk
 
 
 }  // namespace
+
+namespace {
+template <int R, bool LOCAL>
+int launch_gotoh_t(nwb200_ctx* c, const GotohArgs& g)
+{
+    constexpr int W = 4;
+    const size_t smem = (size_t)W * (size_t)c->S * 32 * R;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(nw_gotoh_batch_kernel<R, LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(gotoh)", e);
+    }
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_gotoh_batch_kernel<R, LOCAL>, W * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)c->sm_count * per_sm;
+    const long long need = ((long long)(g.b.npairs - g.b.first) + W - 1) / W;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    nw_gotoh_batch_kernel<R, LOCAL><<<(int)grid, W * 32, smem, c->stream>>>(g);
+    c->launches++;
+    c->batch_kernel = LOCAL ? "nw_gotoh_batch_kernel (local)" : "nw_gotoh_batch_kernel (global)";
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "gotoh batch kernel launch", e);
+    return NWB200_SUCCESS;
+}
+}  // namespace
+
+// affine-gap / local variants (nw_gotoh.cuh): bands of 256 or 512 rows
+int launch_batch_gotoh(nwb200_ctx* c, const GotohArgs& g, bool local)
+{
+    if (g.b.npairs <= g.b.first) return NWB200_SUCCESS;
+    if (c->batch_maxy <= 256) return local ? launch_gotoh_t<8, true>(c, g) : launch_gotoh_t<8, false>(c, g);
+    return local ? launch_gotoh_t<16, true>(c, g) : launch_gotoh_t<16, false>(c, g);
+}
 
 int launch_batch_trace(nwb200_ctx* c, const BatchTraceArgs& a, int need_chunks)
 {

@@ -200,6 +200,8 @@ struct BatchTraceArgs {
 // nw_batch_launch.cu: picks the kernel instance for the resident batch (c->batch_maxy, c->S, c->max_sprime) and launches it on c->stream
 int launch_batch(nwb200_ctx* c, const BatchArgs& a);
 int launch_batch_trace(nwb200_ctx* c, const BatchTraceArgs& a, int need_chunks);
+struct GotohArgs;
+int launch_batch_gotoh(nwb200_ctx* c, const GotohArgs& g, bool local);
 
 }  // namespace nwb
 

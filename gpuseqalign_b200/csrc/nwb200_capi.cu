@@ -8,6 +8,7 @@
 #include "nw_fill.cuh"
 #include "nw_trace.cuh"
 #include "nw_scan.cuh"
+#include "nw_gotoh.cuh"
 
 using namespace nwb;
 

@@ -191,6 +191,17 @@ NWB200_API int  nwb200_upload_batch(nwb200_ctx* ctx, const uint8_t* letters, siz
 NWB200_API int  nwb200_batch_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
 NWB200_API int  nwb200_fetch_batch_scores(nwb200_ctx* ctx, int32_t* scores); /* syncs */
 
+/* Variants the reference lists as future work (README.md:6-29: NW_AG, SW_LG, SW_AG; --gapeCost, cmd_parser.cpp:143,213 is parsed
+ * and unused there): affine gaps (Gotoh) and local alignment (Smith-Waterman) for the RESIDENT batch (nwb200_upload_batch), scores
+ * only, fetched with nwb200_fetch_batch_scores.  A gap of L residues costs gap_open + (L - 1) * gap_extend -- with
+ * gap_extend == gap_open NWB200_VARIANT_NW_AFFINE is the reference's linear-gap recurrence.  No reference implementation exists to
+ * compare with ("parity unpinned" except for that case: DESIGN.md).  Pairs of up to 512 rows, substitution
+ * scores in [-128, 127]. */
+#define NWB200_VARIANT_NW_AFFINE 1
+#define NWB200_VARIANT_SW_LINEAR 2
+#define NWB200_VARIANT_SW_AFFINE 3
+NWB200_API int  nwb200_batch_resident_variant(nwb200_ctx* ctx, int variant, int gap_open, int gap_extend);   /* async on the ctx stream */
+
 /* One very long pair as a cross-GPU wavefront (BASELINE configs 4 and 5; no reference counterpart -- the reference
  * is single-GPU, benchmark.cpp:179).  One context per GPU / process; the columns are dealt to the ranks in blocks of
  * block_cols; border columns travel GPU-to-GPU as peer stores over NVLink into the neighbour's receive buffer, which

@@ -62,6 +62,8 @@ def lib():
                                      C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
         L.nwo_score_batch.restype = C.c_int
         L.nwo_score_batch.argtypes = [_u8p, _u64p, _u32p, _u64p, _u32p, C.c_size_t, _i32p, C.c_int, C.c_int, C.c_int, _i32p]
+        L.nwo_score_batch_gotoh.restype = C.c_int
+        L.nwo_score_batch_gotoh.argtypes = [_u8p, _u64p, _u32p, _u64p, _u32p, C.c_size_t, _i32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _i32p]
         L.nwo_synth_letters.restype = None
         L.nwo_synth_letters.argtypes = [C.c_uint64, _u8p, C.c_size_t]
         _lib = L
@@ -165,6 +167,20 @@ def score_batch(letters: np.ndarray, offY, lenY, offX, lenX, subst: np.ndarray, 
                            substsz, gap, threads, scores)
     if rc != 0:
         raise RuntimeError(f"nwo_score_batch failed rc={rc}")
+    return scores
+
+
+def score_batch_gotoh(letters: np.ndarray, offY, lenY, offX, lenX, subst: np.ndarray, gapo: int, gape: int, local: bool, threads: int = 0) -> np.ndarray:
+    """Affine-gap / Smith-Waterman scores (Gotoh; nw_oracle.c: parity unpinned -- the reference lists these as future work)."""
+    L = lib()
+    n = len(lenY)
+    scores = np.zeros(n, dtype=np.int32)
+    rc = L.nwo_score_batch_gotoh(np.ascontiguousarray(letters, dtype=np.uint8), np.ascontiguousarray(offY, dtype=np.uint64),
+                                 np.ascontiguousarray(lenY, dtype=np.uint32), np.ascontiguousarray(offX, dtype=np.uint64),
+                                 np.ascontiguousarray(lenX, dtype=np.uint32), n, np.ascontiguousarray(subst, dtype=np.int32),
+                                 int(round(len(subst) ** 0.5)), gapo, gape, 1 if local else 0, threads, scores)
+    if rc != 0:
+        raise RuntimeError(f"nwo_score_batch_gotoh failed rc={rc}")
     return scores
 
 

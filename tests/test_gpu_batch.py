@@ -167,3 +167,44 @@ def test_batch_transcripts_kernel(engine, scoring, oracle, n_pairs, max_y, max_x
         assert (scores[p], edits[p], hashes[p]) == (exp.score, exp.edit, exp.trace_hash), p
     if max_x <= 512 and max_y <= 512:
         assert engine.launches() - l0 < 40, "transcripts must not go pair by pair"
+
+
+@pytest.mark.parametrize("max_y,max_x", [(256, 256), (200, 400), (512, 300), (40, 40)])
+def test_batch_affine_and_local_variants(engine, scoring, oracle, max_y, max_x):
+    """The variants the reference lists as future work (README.md:6-29; --gapeCost): Gotoh affine gaps and Smith-Waterman over the
+    resident batch against the CPU restatement (oracle/nw_oracle.c, parity unpinned), and the one case the reference DOES define:
+    affine with gap_extend == gap_open equals its linear-gap recurrence, i.e. the default batch path and the golden-pinned oracle."""
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(7 * max_y + max_x)
+    letters, offY, lenY, offX, lenX = _ragged(rng, 500, max_y, max_x)
+    linear = oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11)
+    assert np.array_equal(engine.align_batch_variant(letters, offY, lenY, offX, lenX, "nw_affine", -11, -11), linear)
+    assert np.array_equal(engine.align_batch(letters, offY, lenY, offX, lenX), linear)
+    for variant, local, go, ge in (("nw_affine", False, -11, -1), ("nw_affine", False, -5, -3), ("sw_affine", True, -11, -1), ("sw_linear", True, -11, -11),
+                                   ("sw_affine", True, -4, 0)):
+        got = engine.align_batch_variant(letters, offY, lenY, offX, lenX, variant, go, ge)
+        exp = oracle.score_batch_gotoh(letters, offY, lenY, offX, lenX, subst, go, ge if variant != "sw_linear" else go, local)
+        assert np.array_equal(got, exp), (variant, go, ge, int(np.count_nonzero(got != exp)))
+
+
+def test_batch_variants_on_similar_sequences_and_errors(engine, scoring, oracle):
+    from gpuseqalign_b200 import NwB200Error, synth
+    subst = scoring["subst"]["blosum62"]
+    # mutated copies: long diagonal runs with indels -- the regime affine gaps are for
+    seqs = []
+    for k in range(64):
+        x = synth.letters(9000 + k, 256)
+        seqs += [synth.mutated_copy(x, 9500 + k, 240 + k % 17), x]
+    lens = np.array([s.size for s in seqs], dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    pool = np.concatenate(seqs + [np.zeros(1, np.uint8)]).astype(np.uint8)
+    offY, offX = offs[0:-1:2].copy(), offs[1::2].copy()
+    lenY, lenX = lens[0::2].astype(np.uint32), lens[1::2].astype(np.uint32)
+    for variant, local in (("nw_affine", False), ("sw_affine", True)):
+        got = engine.align_batch_variant(pool, offY, lenY, offX, lenX, variant, -11, -1)
+        assert np.array_equal(got, oracle.score_batch_gotoh(pool, offY, lenY, offX, lenX, subst, -11, -1, local)), variant
+    with pytest.raises(NwB200Error):
+        engine.batch_resident_variant("nw_affine", 3, -1)             # a positive gap cost
+    bad = pool.copy(); bad[5] = 99
+    with pytest.raises(NwB200Error):
+        engine.align_batch_variant(bad, offY, lenY, offX, lenX, "sw_affine", -11, -1)

@@ -1,7 +1,15 @@
-python -m pytest tests/test_gpu_big.py -m gpu -x -q -k "prefix or cfg4 or scan" 2>&1 | tail -3
-for w in 16 8 4; do
-NWB200_SCAN_WARPS=$w python bench.py --workload scan4m --steps 5 --warmup 3 --no-secondary --no-cpu-baseline > gpurun_out/r2u_scan_w$w.json 2> gpurun_out/r2u_scan_w$w.err; echo rc=$?
-python -c "
-import json
-d=json.loads(open('gpurun_out/r2u_scan_w$w.json').read().strip().splitlines()[-1]); print($w, d['value'], d['ms_per_step'], d['roofline']['frac'], d.get('parity'))"
-done
+python -m pytest tests/test_gpu_batch.py -m gpu -x -q 2>&1 | tail -8
+python - <<'PY'
+import numpy as np, json, time, sys
+sys.path.insert(0,'.')
+from gpuseqalign_b200 import Engine, synth
+subst=np.array(json.load(open('tests/golden/scoring.json'))["subst"]["blosum62"],dtype=np.int32)
+e=Engine(0); e.set_scoring(subst,-11)
+pool,oy,ly,ox,lx=synth.batch_pairs(0,131072,256,256)
+e.upload_batch(pool,oy,ly,ox,lx)
+for v in ("nw_affine","sw_affine","sw_linear"):
+    for _ in range(3):
+        e.batch_resident_variant(v,-11,-1); s=e.fetch_batch_scores()
+    ms=e.timing()["align_calc"]; print(v, round(ms,3),"ms", round(131072*65536/ms/1e6,1),"GCUPS", int(s[:3].sum()))
+e.batch_resident(); s=e.fetch_batch_scores(); print("nw_linear", round(e.timing()["align_calc"],3))
+PY
