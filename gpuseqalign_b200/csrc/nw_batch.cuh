@@ -15,7 +15,14 @@ namespace nwb {
 constexpr unsigned kPastEnd = 0x100u;      // "no letter here" while a byte letter is in flight: distinct from every byte, so that a real
                                            // letter equal to S (the internal zero-row code) is still reported as outside the alphabet
 
-template <int R, int WARPS>
+// TMA = true (A/B switch NWB200_BATCH_TMA=1, north_star: "sequences ... staged into shared memory via TMA"): the column letters
+// reach shared memory as BULK COPIES of the TMA engine (cp.async.bulk global -> shared, 128 columns per copy, two landing buffers per
+// warp, completion on an mbarrier each) instead of one prefetching LDG per lane and chunk; a lane then reads its letter with an
+// LDS.  Needs a 16-byte aligned sequence start (pairs that are not take the LDG path).  Measured: profiles/r2w_* (DESIGN.md).
+constexpr int kTmaBlock = 128;                                   // columns per bulk copy
+__host__ __device__ constexpr size_t batch_tma_warp_bytes() { return 2 * kTmaBlock + 16; }      // two landing buffers + two mbarriers
+
+template <int R, int WARPS, bool TMA = false>
 __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
 {
     constexpr int K = 1;
@@ -26,6 +33,51 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
     stage_sprime(sp_tab, a.sprime, a.S, smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     WarpSmem<R, K> sm(smem_raw + (size_t)w * SC::warp_smem_bytes(a.S), a.S);
+    // TMA: landing buffers and mbarriers of this warp behind the per-warp regions
+    const unsigned land_s = TMA ? (unsigned)__cvta_generic_to_shared(smem_raw + (((size_t)WARPS * SC::warp_smem_bytes(a.S) + 15) & ~(size_t)15) + (size_t)w * batch_tma_warp_bytes()) : 0u;
+    const unsigned mbar_s = land_s + 2 * kTmaBlock;
+    unsigned phase_bits = 0;                          // parity of the next completion of each landing buffer's mbarrier
+    if constexpr (TMA) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar_s + 8u) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // lane 0: bulk copy of block kb (columns 128 kb ..) of x into its landing buffer; bytes rounded up to 16 (the pool has slack)
+    auto tma_issue = [&](const uint8_t* x, int m, int kb) {
+        if constexpr (TMA) {
+            const int c0 = kTmaBlock * kb;
+            if (lane == 0 && c0 < m) {
+                const unsigned bytes = (unsigned)((min(kTmaBlock, m - c0) + 15) & ~15);
+                const unsigned dst = land_s + (unsigned)(kb & 1) * kTmaBlock, mb = mbar_s + 8u * (unsigned)(kb & 1);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(x + c0), "r"(bytes), "r"(mb) : "memory");
+            }
+        }
+    };
+    // all lanes: wait until block kb has landed
+    auto tma_wait = [&](int m, int kb) {
+        if constexpr (TMA) {
+            if (kTmaBlock * kb < m) {
+                const unsigned mb = mbar_s + 8u * (unsigned)(kb & 1), par = (phase_bits >> (kb & 1)) & 1u;
+                unsigned done = 0, polls = 0;
+                while (!done) {
+                    asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.b32 %0, 1, 0, P1;\n\t}"
+                                 : "=r"(done) : "r"(mb), "r"(par) : "memory");
+                    if (++polls > (1u << 22)) { g_wait_timeout = 1; break; }
+                }
+                phase_bits ^= 1u << (kb & 1);
+            }
+        }
+    };
+    auto tma_letter = [&](int c) -> unsigned {      // letter of column c from its landing buffer
+        unsigned v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(land_s + (unsigned)(c & (2 * kTmaBlock - 1))));
+        return v;
+    };
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     ChunkIO io;
     io.prof_lane = sm.prof + lane * 4 * SC::WPL;
@@ -49,11 +101,14 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
             const int i = lane * R - pad + r;
             if (i >= 0 && i < n && (unsigned)__ldg(y + i) >= (unsigned)a.S) *a.err = 1;
         }
+        const bool bulk = TMA && ((reinterpret_cast<unsigned long long>(x) & 15ull) == 0ull);      // (warp-uniform)
+        if (bulk) { tma_issue(x, m, 0); tma_issue(x, m, 1); }      // land under the profile build
         build_profile<R, K>(sm, sp_tab, a.S, y, (long long)lane * R - pad, n, lane, nullptr);
         for (int c = -32 + lane; c < 0; c += 32) sm.put_letter(c, ZOFF);
+        if (bulk) tma_wait(m, 0);
         for (int g = 0; g < PD; g++) {
             const int c = 32 * g + lane;
-            unsigned v = c < m ? (unsigned)__ldg(x + c) : kPastEnd;
+            unsigned v = c < m ? (bulk ? tma_letter(c) : (unsigned)__ldg(x + c)) : kPastEnd;
             if (v >= (unsigned)a.S) { if (v != kPastEnd) *a.err = 1; v = (unsigned)a.S; }      // a real letter must be < S
             sm.put_letter(c, v * SC::LSTRIDE);
         }
@@ -65,13 +120,27 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch_kernel(const BatchArgs a)
         const int nlc = SC::nlc(m);
         for (int lc = 0; lc < nlc; lc++) {
             const int cp = 32 * (lc + PD) + lane;
-            unsigned pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : kPastEnd;           // checked and scaled when it lands
+            unsigned pf_x;
+            if (bulk) {
+                const int g = lc + PD;                                             // group of 32 columns fetched now: block g / 4
+                if ((g & 3) == 0) tma_wait(m, g >> 2);
+                pf_x = (cp < m) ? tma_letter(cp) : kPastEnd;
+                if ((g & 3) == 3) { __syncwarp(); tma_issue(x, m, (g >> 2) + 2); }     // every lane has read this block: its buffer takes the block after next
+            } else {
+                pf_x = (cp < m) ? (unsigned)__ldg(x + cp) : kPastEnd;             // checked and scaled when it lands
+            }
             io.xs_lane = sm.xs + ((32 * lc - K * lane) & (XR - 1));
             sweep_chunk<R, K, 0, false>(st, lane, io, nullptr);
             __syncwarp();
             if (pf_x >= (unsigned)a.S) { if (pf_x != kPastEnd) *a.err = 1; pf_x = (unsigned)a.S; }
             sm.put_letter(cp, pf_x * SC::LSTRIDE);
             __syncwarp();
+        }
+        if (bulk) {
+            // copies that were issued for blocks the sweep never read (the last groups lie past the end of x) must land before the
+            // buffers are reused: wait for every block that was requested
+            const int last_read = (nlc - 1 + PD) >> 2, last_issued = ((nlc - 1 + PD) >> 2) + 1 + (((nlc - 1 + PD) & 3) == 3 ? 1 : 0);
+            for (int kb = last_read + 1; kb <= last_issued; kb++) tma_wait(m, kb);
         }
         // lane 31's last row is row n of the matrix, frozen at column m: un-shift H = P + (n+m)*gap
         if (lane == 31) a.scores[p] = st.h[R - 1] + (n + m) * a.gap;

@@ -9,25 +9,26 @@
 namespace nwb {
 namespace {
 
-template <int R>
+template <int R, bool TMA = false>
 int launch_batch_t(nwb200_ctx* c, const BatchArgs& a)
 {
     constexpr int W = 4;
     size_t smem = Sched<R, 1>::warp_smem_bytes(c->S) * W;
+    if (TMA) smem = ((smem + 15) & ~(size_t)15) + W * batch_tma_warp_bytes();
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(nw_batch_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(nw_batch_kernel<R, W, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "cudaFuncSetAttribute(batch)", e);
     }
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_batch_kernel<R, W>, W * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_batch_kernel<R, W, TMA>, W * 32, smem);
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)c->sm_count * per_sm;
     const long long need = ((long long)(a.npairs - a.first) + W - 1) / W;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    nw_batch_kernel<R, W><<<(int)grid, W * 32, smem, c->stream>>>(a);
+    nw_batch_kernel<R, W, TMA><<<(int)grid, W * 32, smem, c->stream>>>(a);
     c->launches++;
-    c->batch_kernel = "nw_batch_kernel";
+    c->batch_kernel = TMA ? "nw_batch_kernel (letters by TMA bulk copies)" : "nw_batch_kernel";
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "batch kernel launch", e);
     return NWB200_SUCCESS;
@@ -169,6 +170,14 @@ int launch_batch(nwb200_ctx* c, const BatchArgs& a)
         if (v == 7) return launch_batch3_t<8, 2, 1, 32, false, true>(c, a);      // profiles two rows per word: the merge is an integer add
         if (v == 6) return launch_batch3_t<16, 4, 1, 16, true>(c, a);      // four pairs per warp, every lane cut into two half-lanes a column apart
         return launch_batch3_t<8, 2, 1>(c, a);
+    }
+    {
+        const char* e = getenv("NWB200_BATCH_TMA");        // developer switch (A/B): column letters staged by TMA bulk copies
+        if (e && e[0] == '1') {
+            if (c->batch_maxy <= 128) return launch_batch_t<4, true>(c, a);
+            if (c->batch_maxy <= 256) return launch_batch_t<8, true>(c, a);
+            return launch_batch_t<16, true>(c, a);
+        }
     }
     if (c->batch_maxy <= 128) return launch_batch_t<4>(c, a);
     if (c->batch_maxy <= 256) return launch_batch_t<8>(c, a);

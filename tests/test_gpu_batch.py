@@ -115,6 +115,13 @@ def test_batch_packed_and_32bit_kernels_agree(engine, scoring, oracle, monkeypat
     monkeypatch.setenv("NWB200_BATCH_PACKED", "0")
     plain = engine.align_batch(letters, offY, lenY, offX, lenX)
     assert np.array_equal(plain, exp)
+    # the 32-bit kernel with its column letters staged by TMA bulk copies (ragged offsets: most pairs are not 16-byte aligned and take
+    # the LDG path inside the same launch; the aligned synthetic batch below takes the bulk path for every pair)
+    monkeypatch.setenv("NWB200_BATCH_TMA", "1")
+    assert np.array_equal(engine.align_batch(letters, offY, lenY, offX, lenX), exp)
+    from gpuseqalign_b200 import synth
+    pool, oY, lY, oX, lX = synth.batch_pairs(40 + n_pairs, 300, 256, 256)
+    assert np.array_equal(engine.align_batch(pool, oY, lY, oX, lX), oracle.score_batch(pool, oY, lY, oX, lX, subst, -11))
 
 
 def test_batch_packed_halves_at_their_bound(scoring, oracle):
