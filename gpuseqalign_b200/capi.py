@@ -92,7 +92,7 @@ EXPORTS = [
     "nwb200_get_timing", "nwb200_stream", "nwb200_sync", "nwb200_kernel_launches", "nwb200_version",
     "nwb200_wave_upload", "nwb200_wave_export", "nwb200_wave_connect", "nwb200_wave_fill", "nwb200_wave_fetch",
     "nwb200_scan_upload", "nwb200_scan_fill", "nwb200_scan_fetch", "nwb200_batch_kernel_name",
-    "nwb200_batch_resident_variant", "nwb200_trace_info", "nwb200_wave_keep_headers", "nwb200_wave_export_headers", "nwb200_wave_connect_headers", "nwb200_wave_gather_headers",
+    "nwb200_batch_resident_variant", "nwb200_align_batch_packed5", "nwb200_upload_batch_packed5", "nwb200_trace_info", "nwb200_wave_keep_headers", "nwb200_wave_export_headers", "nwb200_wave_connect_headers", "nwb200_wave_gather_headers",
     "nwb200_upload_pair_i32", "nwb200_get_hdr_info", "nwb200_score_rows", "nwb200_trace_values", "nwb200_get_memory_usage",
 ]
 
@@ -147,6 +147,8 @@ def load_library():
     L.nwb200_get_memory_usage.argtypes = [vp, P(_MemUsage)]
     L.nwb200_trace_info.argtypes = [vp, P(C.c_int), P(C.c_int), P(C.c_int)]
     L.nwb200_batch_resident_variant.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.nwb200_align_batch_packed5.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_size_t, vp]
+    L.nwb200_upload_batch_packed5.argtypes = [vp, vp, C.c_size_t, vp, vp, vp, vp, C.c_size_t]
     L.nwb200_wave_keep_headers.argtypes = [vp, C.c_int]
     L.nwb200_wave_export_headers.argtypes = [vp, vp, vp]
     L.nwb200_wave_connect_headers.argtypes = [vp, vp, vp]
@@ -319,6 +321,23 @@ class Engine:
         lenY = np.ascontiguousarray(lenY, dtype=np.uint32); lenX = np.ascontiguousarray(lenX, dtype=np.uint32)
         self._npairs = lenY.size
         self._check(self._L.nwb200_upload_batch(self._h, _ptr(letters), letters.size, _ptr(offY), _ptr(lenY), _ptr(offX), _ptr(lenX), lenY.size))
+
+    def upload_batch_packed5(self, packed, offY, lenY, offX, lenX):
+        """Resident batch from 5-bit packed letters (synth.pack5): byte offsets of the sequences' bit streams, lengths in letters."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offY = np.ascontiguousarray(offY, dtype=np.uint64); offX = np.ascontiguousarray(offX, dtype=np.uint64)
+        lenY = np.ascontiguousarray(lenY, dtype=np.uint32); lenX = np.ascontiguousarray(lenX, dtype=np.uint32)
+        self._npairs = lenY.size
+        self._check(self._L.nwb200_upload_batch_packed5(self._h, _ptr(packed), packed.size, _ptr(offY), _ptr(lenY), _ptr(offX), _ptr(lenX), lenY.size))
+
+    def align_batch_packed5(self, packed, offY, lenY, offX, lenX, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Scores of a batch whose letters arrive 5-bit packed, from host buffers (the slice pipeline of align_batch)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        offY = np.ascontiguousarray(offY, dtype=np.uint64); offX = np.ascontiguousarray(offX, dtype=np.uint64)
+        lenY = np.ascontiguousarray(lenY, dtype=np.uint32); lenX = np.ascontiguousarray(lenX, dtype=np.uint32)
+        scores = out if out is not None else np.empty(lenY.size, dtype=np.int32)
+        self._check(self._L.nwb200_align_batch_packed5(self._h, _ptr(packed), packed.size, _ptr(offY), _ptr(lenY), _ptr(offX), _ptr(lenX), lenY.size, _ptr(scores)))
+        return scores
 
     def batch_resident(self):
         self._check(self._L.nwb200_batch_resident(self._h))

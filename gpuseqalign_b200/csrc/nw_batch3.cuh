@@ -88,15 +88,43 @@ __device__ __forceinline__ uint4 b3_lds128(unsigned addr)
     return v;
 }
 
+// ---- 5-bit packed letters (PK instances; include/nwb200.h, nwb200_align_batch_packed5): letter k of a sequence sits in bits
+// [5k, 5k + 5) of the little-endian bit stream that starts at the sequence's BYTE offset in the pool (8 letters in 5 bytes).  The
+// pool is allocated with slack, so aligned 32-bit loads may run a few bytes past a sequence's end.
+// 32 bits of the stream starting at bit `bit` (any alignment)
+__device__ __forceinline__ unsigned b3_bits32(const uint8_t* __restrict__ base, long long bit)
+{
+    const uint8_t* p = base + (bit >> 3);
+    const unsigned long long ad = reinterpret_cast<unsigned long long>(p);
+    const unsigned* w = reinterpret_cast<const unsigned*>(ad & ~3ull);
+    const unsigned sh = (unsigned)(ad & 3ull) * 8u + (unsigned)(bit & 7);
+    const unsigned w0 = __ldg(w), w1 = __ldg(w + 1);
+    return __funnelshift_r(w0, w1, sh);              // sh <= 31
+}
+// four 5-bit letters (the low 20 bits of v) -> one letter per byte
+__device__ __forceinline__ unsigned b3_unpack4(unsigned v)
+{
+    return (v & 31u) | ((v << 3) & 0x1f00u) | ((v << 6) & 0x1f0000u) | ((v << 9) & 0x1f000000u);
+}
+
 // The R row letters of a lane, fetched ahead of their use (for the NEXT pair of a warp while the current one is swept): a lane whose
 // R = 8 rows are all inside the sequence and 8-byte aligned fetches them with one load (`fast`); other lanes fetch when they build.
 struct B3Rows { uint4 v; bool fast; };
-template <int R>
+template <int R, bool PK = false>
 __device__ __forceinline__ B3Rows b3_fetch_rows(const uint8_t* __restrict__ y, int i0, int n)
 {
     B3Rows q;
     q.v = make_uint4(0u, 0u, 0u, 0u);
     q.fast = false;
+    if constexpr (PK) {                              // any alignment: R letters = 5 R bits from bit 5 i0
+        static_assert(!PK || R == 8, "packed letters: 8 rows per lane");
+        q.fast = i0 >= 0 && i0 + 8 <= n;
+        if (q.fast) {
+            const unsigned lo = b3_bits32(y, 5LL * i0), hi = b3_bits32(y, 5LL * i0 + 20);
+            q.v.x = b3_unpack4(lo); q.v.y = b3_unpack4(hi);
+        }
+        return q;
+    }
     if constexpr (R == 8) {
         q.fast = i0 >= 0 && i0 + 8 <= n && ((reinterpret_cast<unsigned long long>(y + i0) & 7ull) == 0ull);
         if (q.fast) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(y + i0)); q.v.x = t.x; q.v.y = t.y; }
@@ -109,7 +137,7 @@ __device__ __forceinline__ B3Rows b3_fetch_rows(const uint8_t* __restrict__ y, i
 }
 
 // Row offsets (bytes into an s' table) of a lane's R matrix rows; row S = the zero row for padding rows.  Returns true when a letter is >= S.
-template <int R>
+template <int R, bool PK = false>
 __device__ __forceinline__ bool b3_table_rows(unsigned* row_off, int S, const uint8_t* __restrict__ y, int i0, int n, const B3Rows& pre)
 {
     unsigned yl[R];
@@ -120,7 +148,8 @@ __device__ __forceinline__ bool b3_table_rows(unsigned* row_off, int S, const ui
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int i = i0 + r;
-            yl[r] = (i >= 0 && i < n) ? (unsigned)__ldg(y + i) : kPastEnd;
+            if constexpr (PK) yl[r] = (i >= 0 && i < n) ? (b3_bits32(y, 5LL * i) & 31u) : kPastEnd;
+            else yl[r] = (i >= 0 && i < n) ? (unsigned)__ldg(y + i) : kPastEnd;
         }
     }
     bool bad = false;
@@ -212,7 +241,7 @@ __device__ __forceinline__ void b3_build_profile_exp(unsigned prof_lane_s, unsig
     }
 }
 
-template <int R, int WARPS, int MQ, int K = 1, int G = 32, bool SPLIT = false, bool EXP = false>
+template <int R, int WARPS, int MQ, int K = 1, int G = 32, bool SPLIT = false, bool EXP = false, bool PK = false>
 __global__ void __launch_bounds__(WARPS * 32) nw_batch3_kernel(const BatchArgs a)
 {
     using S3 = Sched3<R, K, G, SPLIT, EXP>;
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch3_kernel(const BatchArgs a
     // the row letters of a pair are requested as soon as its metadata is known: one pair ahead of the sweep
     auto fetch_rows = [&](unsigned long long off, unsigned n) {
         const int nn = n > (unsigned)By ? 0 : (int)n;             // taller than the band: swept as an empty pair
-        return b3_fetch_rows<R>(a.letters + off, gl * R - (By - nn), nn);
+        return b3_fetch_rows<R, PK>(a.letters + off, gl * R - (By - nn), nn);
     };
     unsigned long long tk = 0;                       // lane 0: the ticket drawn ahead
     if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
@@ -294,6 +323,7 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch3_kernel(const BatchArgs a
         const bool al = (((reinterpret_cast<unsigned long long>(xA) | reinterpret_cast<unsigned long long>(xB)) & 3ull) == 0ull);
         auto fetch4 = [&](const uint8_t* x, int mm, int c0) -> unsigned {
             if (c0 >= mm) return 0u;
+            if constexpr (PK) return b3_unpack4(b3_bits32(x, 5LL * c0));      // (letters past the end are masked out below)
             if (al) return __ldg(reinterpret_cast<const unsigned*>(x + c0));
             unsigned v = 0u;
 #pragma unroll
@@ -335,10 +365,10 @@ __global__ void __launch_bounds__(WARPS * 32) nw_batch3_kernel(const BatchArgs a
         //      scribbles on the zero row and pair B's first rows; pair B's on the start of the ring; zero row and ring come last.
         {
             unsigned ro[R];
-            const bool badA = b3_table_rows<R>(ro, S, yA, gl * R - (By - nA), nA, crA);
+            const bool badA = b3_table_rows<R, PK>(ro, S, yA, gl * R - (By - nA), nA, crA);
             if constexpr (EXP) b3_build_profile_exp<R, false>(laneA_s, tabA_s, S, ro);
             else b3_build_profile<R>(laneA_s, tabA_s, S, ro);
-            const bool badB = b3_table_rows<R>(ro, S, yB, gl * R - (By - nB), nB, crB);
+            const bool badB = b3_table_rows<R, PK>(ro, S, yB, gl * R - (By - nB), nB, crB);
             if constexpr (EXP) b3_build_profile_exp<R, true>(laneB_s, tabB_s, S, ro);
             else b3_build_profile<R>(laneB_s, tabB_s, S, ro);
             if (badA || badB) *a.err = 1;

@@ -92,7 +92,7 @@ int launch_batch2_t(nwb200_ctx* c, const BatchArgs& a)
 }
 
 // Round-2 packed kernel (nw_batch3.cuh): same CTA-shape search.  G = lanes per packed pair of pairs (32: two pairs per warp, 16: four).
-template <int R, int W, int MQ, int K, int G, bool SPLIT, bool EXP>
+template <int R, int W, int MQ, int K, int G, bool SPLIT, bool EXP, bool PK>
 int launch_batch3_w(nwb200_ctx* c, const BatchArgs& a, size_t smem, int per_sm)
 {
     constexpr int PPW = 2 * (32 / G);                             // pairs per warp and ticket
@@ -100,28 +100,28 @@ int launch_batch3_w(nwb200_ctx* c, const BatchArgs& a, size_t smem, int per_sm)
     const long long need = ((long long)(a.npairs - a.first) + PPW * W - 1) / (PPW * W);
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP><<<(int)grid, W * 32, smem, c->stream>>>(a);
+    nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP, PK><<<(int)grid, W * 32, smem, c->stream>>>(a);
     c->launches++;
-    c->batch_kernel = EXP ? "nw_batch3_kernel (expanded profiles)" : SPLIT ? "nw_batch3_kernel (four pairs per warp, split lanes)" : G == 16 ? "nw_batch3_kernel (four pairs per warp)" : K == 2 ? "nw_batch3_kernel (K = 2)" : (MQ == R / 4 ? "nw_batch3_kernel" : "nw_batch3_kernel (mixed IDP routes)");
+    c->batch_kernel = PK ? "nw_batch3_kernel (5-bit packed letters)" : EXP ? "nw_batch3_kernel (expanded profiles)" : SPLIT ? "nw_batch3_kernel (four pairs per warp, split lanes)" : G == 16 ? "nw_batch3_kernel (four pairs per warp)" : K == 2 ? "nw_batch3_kernel (K = 2)" : (MQ == R / 4 ? "nw_batch3_kernel" : "nw_batch3_kernel (mixed IDP routes)");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(c, NWB200_ERR_KERNEL_FAILURE, "packed batch kernel launch", e);
     return NWB200_SUCCESS;
 }
 
-template <int R, int W, int MQ, int K, int G, bool SPLIT, bool EXP>
+template <int R, int W, int MQ, int K, int G, bool SPLIT, bool EXP, bool PK>
 int batch3_occupancy(nwb200_ctx* c, size_t* smem_out)
 {
     const size_t smem = Sched3<R, K, G, SPLIT, EXP>::warp_smem_bytes(c->S) * W;
     *smem_out = smem;
     if (smem > 48 * 1024) {
-        if (cudaFuncSetAttribute(nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+        if (cudaFuncSetAttribute(nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     }
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP>, W * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nw_batch3_kernel<R, W, MQ, K, G, SPLIT, EXP, PK>, W * 32, smem) != cudaSuccess) { cudaGetLastError(); return 0; }
     return per_sm;
 }
 
-template <int R, int MQ, int K, int G = 32, bool SPLIT = false, bool EXP = false>
+template <int R, int MQ, int K, int G = 32, bool SPLIT = false, bool EXP = false, bool PK = false>
 int launch_batch3_t(nwb200_ctx* c, const BatchArgs& a)
 {
     struct Choice { int S = -1, w = 0, per_sm = 0; size_t smem = 0; };
@@ -129,7 +129,7 @@ int launch_batch3_t(nwb200_ctx* c, const BatchArgs& a)
     Choice& ch = choices[c->device & 63];
     if (ch.S != c->S) {
         size_t s4 = 0, s8 = 0, s16 = 0;
-        const int o4 = batch3_occupancy<R, 4, MQ, K, G, SPLIT, EXP>(c, &s4), o8 = batch3_occupancy<R, 8, MQ, K, G, SPLIT, EXP>(c, &s8), o16 = batch3_occupancy<R, 16, MQ, K, G, SPLIT, EXP>(c, &s16);
+        const int o4 = batch3_occupancy<R, 4, MQ, K, G, SPLIT, EXP, PK>(c, &s4), o8 = batch3_occupancy<R, 8, MQ, K, G, SPLIT, EXP, PK>(c, &s8), o16 = batch3_occupancy<R, 16, MQ, K, G, SPLIT, EXP, PK>(c, &s16);
         const char* force = getenv("NWB200_BATCH_WARPS");      // developer switch
         const int fw = force ? atoi(force) : 0;
         int best = 0;
@@ -139,9 +139,9 @@ int launch_batch3_t(nwb200_ctx* c, const BatchArgs& a)
         if (best == 0) return fail(c, NWB200_ERR_KERNEL_FAILURE, "packed batch kernel does not fit an SM");
         ch.S = c->S;
     }
-    if (ch.w == 4) return launch_batch3_w<R, 4, MQ, K, G, SPLIT, EXP>(c, a, ch.smem, ch.per_sm);
-    if (ch.w == 8) return launch_batch3_w<R, 8, MQ, K, G, SPLIT, EXP>(c, a, ch.smem, ch.per_sm);
-    return launch_batch3_w<R, 16, MQ, K, G, SPLIT, EXP>(c, a, ch.smem, ch.per_sm);
+    if (ch.w == 4) return launch_batch3_w<R, 4, MQ, K, G, SPLIT, EXP, PK>(c, a, ch.smem, ch.per_sm);
+    if (ch.w == 8) return launch_batch3_w<R, 8, MQ, K, G, SPLIT, EXP, PK>(c, a, ch.smem, ch.per_sm);
+    return launch_batch3_w<R, 16, MQ, K, G, SPLIT, EXP, PK>(c, a, ch.smem, ch.per_sm);
 }
 
 bool batch_packed_enabled()
@@ -155,6 +155,12 @@ bool batch_packed_enabled()
 int launch_batch(nwb200_ctx* c, const BatchArgs& a)
 {
     if (a.npairs <= a.first) return NWB200_SUCCESS;
+    if (a.packed5) {
+        // 5-bit packed letters are read by the packed-halves kernel only
+        if (!(c->max_sprime <= kBatch3MaxSprime && c->S <= kBatch3MaxLetters && c->batch_maxy <= 256))
+            return fail(c, NWB200_ERR_INVALID_VALUE, "5-bit packed letters need at most 31 letters, subst - 2*gap <= 127 and pairs of at most 256 rows");
+        return launch_batch3_t<8, 2, 1, 32, false, false, true>(c, a);
+    }
     // packed halves: P <= min(n, m) * max s' <= 256 * 127 fits 15 bits and 512 * s' fits 16 (nw_batch2.cuh)
     if (c->max_sprime <= kBatch3MaxSprime && c->S <= kBatch3MaxLetters && c->batch_maxy <= 256 && batch_packed_enabled())
     {

@@ -136,6 +136,7 @@ struct nwb200_ctx {
     unsigned epoch = 0;
     int launches = 0;
     const char* batch_kernel = "";
+    bool batch_packed5 = false;          // the resident batch holds 5-bit packed letters
     int corr_w = 0, corr_nseg = 0;      // the last traceback: segments per band of the corridor pass (0: none) out of corr_nseg
     int* d_miss = nullptr;              // its miss flag (device)
     // resources of the last fill launch (nwb200_get_memory_usage; the reference's updateNwAlgPeakMemUsage, nwalign_shared.cpp:5-25)
@@ -175,6 +176,7 @@ struct BatchArgs {
     int gap;
     int* scores;                         // H[lenY][lenX] per pair; kBatchTooTall if lenY > 32*R (the host re-runs those as single pairs)
     unsigned long long* ticket;          // zero at launch
+    int packed5;                         // 1: the letters are 5-bit packed (8 letters in 5 bytes), offsets are BYTE offsets of the sequences' bit streams
     int* err;                            // set to 1 when a letter outside the alphabet is met (the pair's score is then meaningless), 2 when the
                                          // s' table did not arrive
 };

@@ -76,3 +76,40 @@ def batch_pairs(first_pair: int, n_pairs: int, len_y: int, len_x: int):
     lenX = np.full(n_pairs, len_x, dtype=np.uint32)
     lenY = np.full(n_pairs, len_y, dtype=np.uint32)
     return pool.reshape(-1), offY, lenY, offX, lenX
+
+
+def pack5(letters: np.ndarray, offs: np.ndarray, lens: np.ndarray):
+    """5-bit packing of the sequences of a byte pool (what nwb200_align_batch_packed5 takes): sequence k -- `lens[k]` letters at
+    `letters[offs[k]:]` -- becomes a little-endian bit stream of 5 bits per letter that starts at byte `new_offs[k]` of the packed
+    pool (8 letters in 5 bytes; every sequence starts on a byte).  Returns (packed pool with 64 bytes of slack, new_offs)."""
+    letters = np.ascontiguousarray(letters, dtype=np.uint8)
+    offs = np.asarray(offs, dtype=np.int64); lens = np.asarray(lens, dtype=np.int64)
+    nbytes = (lens * 5 + 7) // 8
+    new_offs = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.uint64) if lens.size else np.zeros(0, np.uint64)
+    total = int(nbytes.sum())
+    out = np.zeros(total + 64, dtype=np.uint8)
+    if lens.size == 0:
+        return out, new_offs
+    if np.all(lens == lens[0]) and lens[0] % 8 == 0 and lens[0] > 0:      # equal lengths, whole groups of 8 letters: one vectorised pass
+        L = int(lens[0])
+        idx = offs[:, None] + np.arange(L, dtype=np.int64)[None, :]
+        v = letters[idx].reshape(lens.size, L // 8, 8).astype(np.uint64)
+        word = np.zeros((lens.size, L // 8), dtype=np.uint64)
+        for k in range(8):
+            word |= (v[:, :, k] & np.uint64(31)) << np.uint64(5 * k)
+        b = np.empty((lens.size, L // 8, 5), dtype=np.uint8)
+        for k in range(5):
+            b[:, :, k] = ((word >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+        out[:total] = b.reshape(-1)
+        return out, new_offs
+    for k in range(lens.size):                                             # ragged: sequence by sequence
+        L = int(lens[k])
+        if L == 0:
+            continue
+        v = letters[int(offs[k]): int(offs[k]) + L].astype(np.uint64) & np.uint64(31)
+        bits = ((v[:, None] >> np.arange(5, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1)
+        pad = (-bits.size) % 8
+        if pad:
+            bits = np.concatenate([bits, np.zeros(pad, np.uint8)])
+        out[int(new_offs[k]): int(new_offs[k]) + int(nbytes[k])] = np.packbits(bits, bitorder="little")
+    return out, new_offs

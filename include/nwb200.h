@@ -191,6 +191,15 @@ NWB200_API int  nwb200_upload_batch(nwb200_ctx* ctx, const uint8_t* letters, siz
 NWB200_API int  nwb200_batch_resident(nwb200_ctx* ctx);                      /* async on the ctx stream */
 NWB200_API int  nwb200_fetch_batch_scores(nwb200_ctx* ctx, int32_t* scores); /* syncs */
 
+/* The same batch calls with 5-bit PACKED letters: `packed` holds, from byte offY[p] / offX[p] on, the little-endian bit stream of a
+ * sequence's letters, 5 bits each (8 letters in 5 bytes; a sequence of L letters occupies ceil(5 L / 8) bytes); n_bytes = size of the
+ * pool.  Scores only.  The one-shot call is bound by the host-to-device copy of the letters: packing takes 3/8 of it away.  Needs an
+ * alphabet of at most 31 letters, subst - 2*gap <= 127 and pairs of at most 256 rows (the packed-halves kernel reads the stream). */
+NWB200_API int  nwb200_align_batch_packed5(nwb200_ctx* ctx, const uint8_t* packed, size_t n_bytes, const uint64_t* offY, const uint32_t* lenY,
+                                           const uint64_t* offX, const uint32_t* lenX, size_t n_pairs, int32_t* scores);
+NWB200_API int  nwb200_upload_batch_packed5(nwb200_ctx* ctx, const uint8_t* packed, size_t n_bytes, const uint64_t* offY, const uint32_t* lenY,
+                                            const uint64_t* offX, const uint32_t* lenX, size_t n_pairs);
+
 /* Variants the reference lists as future work (README.md:6-29: NW_AG, SW_LG, SW_AG; --gapeCost, cmd_parser.cpp:143,213 is parsed
  * and unused there): affine gaps (Gotoh) and local alignment (Smith-Waterman) for the RESIDENT batch (nwb200_upload_batch), scores
  * only, fetched with nwb200_fetch_batch_scores.  A gap of L residues costs gap_open + (L - 1) * gap_extend -- with

@@ -215,3 +215,46 @@ def test_batch_variants_on_similar_sequences_and_errors(engine, scoring, oracle)
     bad = pool.copy(); bad[5] = 99
     with pytest.raises(NwB200Error):
         engine.align_batch_variant(bad, offY, lenY, offX, lenX, "sw_affine", -11, -1)
+
+
+def _pack_batch(letters, offY, lenY, offX, lenX):
+    """Packs the sequences of a batch (Y and X of every pair, in pool order) into one 5-bit pool; returns (packed, offY, offX)."""
+    from gpuseqalign_b200 import synth
+    n = len(lenY)
+    offs = np.empty(2 * n, dtype=np.int64); lens = np.empty(2 * n, dtype=np.int64)
+    offs[0::2] = offY; offs[1::2] = offX; lens[0::2] = lenY; lens[1::2] = lenX
+    packed, noffs = synth.pack5(letters, offs, lens)
+    return packed, noffs[0::2].copy(), noffs[1::2].copy()
+
+
+@pytest.mark.parametrize("n_pairs,max_y,max_x", [(1, 256, 256), (601, 256, 300), (333, 100, 60), (64, 7, 9)])
+def test_batch_packed5_letters(engine, scoring, oracle, n_pairs, max_y, max_x):
+    """5-bit packed letters (8 letters in 5 bytes, every sequence on a byte boundary) through both batch forms: ragged lengths (row
+    groups that straddle bytes, empty sequences, odd pair counts) and the aligned synthetic batch; equal to the byte-letter scores."""
+    from gpuseqalign_b200 import NwB200Error, synth
+    subst = scoring["subst"]["blosum62"]
+    rng = np.random.default_rng(5000 + n_pairs)
+    letters, offY, lenY, offX, lenX = _ragged(rng, n_pairs, max_y, max_x)
+    exp = oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11)
+    packed, pY, pX = _pack_batch(letters, offY, lenY, offX, lenX)
+    assert np.array_equal(engine.align_batch_packed5(packed, pY, lenY, pX, lenX), exp)
+    engine.upload_batch_packed5(packed, pY, lenY, pX, lenX)
+    engine.batch_resident()
+    assert np.array_equal(engine.fetch_batch_scores(), exp)
+    with pytest.raises(NwB200Error):
+        engine.batch_resident_variant("nw_affine", -11, -1)            # the variants take byte letters
+    pool, oY, lY, oX, lX = synth.batch_pairs(77, 70000, 256, 256)           # several H2D slices
+    packed, pY, pX = _pack_batch(pool, oY, lY, oX, lX)
+    assert packed.size < pool.size * 0.63
+    got = engine.align_batch_packed5(packed, pY, lY, pX, lX)
+    assert np.array_equal(got, engine.align_batch(pool, oY, lY, oX, lX))
+    assert np.array_equal(got[:3000], oracle.score_batch(pool[: 3000 * 512], oY[:3000], lY[:3000], oX[:3000], lX[:3000], subst, -11))
+    bad = letters.copy()
+    if bad.size > 3 and lenY[0] > 0:
+        bad[int(offY[0])] = 27                                           # a 5-bit value outside the 25-letter alphabet
+        packed, pY, pX = _pack_batch(bad, offY, lenY, offX, lenX)
+        with pytest.raises(NwB200Error):
+            engine.align_batch_packed5(packed, pY, lenY, pX, lenX)
+    tall_y = np.array([300], dtype=np.uint32)
+    with pytest.raises(NwB200Error):
+        engine.align_batch_packed5(np.zeros(1024, np.uint8), np.array([0], np.uint64), tall_y, np.array([400], np.uint64), np.array([10], np.uint32))
