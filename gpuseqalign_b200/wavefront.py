@@ -57,6 +57,8 @@ def wave_trace_setup(engine, y: np.ndarray, x: np.ndarray, *, rank: int = 0, wor
     snapshots of its column blocks, the tracer maps them all.  block_cols must be a multiple of the snapshot spacing (512 columns for
     pairs longer than 65 536, 256 below, or params.tile_cols)."""
     import torch.distributed as dist
+    if world < 2:
+        raise ValueError("wave_trace_setup is for world > 1; on one GPU use Engine.align(y, x, keep_headers=True) and Engine.trace()")
     engine.wave_keep_headers(True)
     try:
         handle = engine.wave_upload(y, x, rank, world, block_cols, params)

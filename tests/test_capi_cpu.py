@@ -54,3 +54,21 @@ def test_product_never_imports_oracle():
                     if re.search(r"nw_oracle|pyoracle|libnworacle|libnwref|oracle/", txt):
                         bad.append(os.path.join(dp, fn))
     assert bad == []
+
+
+def test_pack5_round_trip():
+    """synth.pack5 (the host side of nwb200_align_batch_packed5): 8 letters in 5 bytes, little-endian bit stream, every sequence on a byte
+    boundary; the vectorised path (equal lengths, multiples of 8) and the sequence-by-sequence path agree with a bit-level unpack."""
+    import numpy as np
+    from gpuseqalign_b200 import synth
+    rng = np.random.default_rng(5)
+    pool = rng.integers(0, 25, 5000).astype(np.uint8)
+    for lens in (np.full(12, 256), np.array([0, 1, 7, 8, 9, 255, 256, 257, 31, 64, 3, 100])):
+        offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        packed, noffs = synth.pack5(pool, offs, lens)
+        assert packed.size == int(((lens * 5 + 7) // 8).sum()) + 64
+        for k in range(lens.size):
+            L = int(lens[k])
+            raw = packed[int(noffs[k]): int(noffs[k]) + (5 * L + 7) // 8]
+            bits = np.unpackbits(raw, bitorder="little")[: 5 * L].reshape(L, 5)
+            assert np.array_equal((bits * (1 << np.arange(5))).sum(1), pool[int(offs[k]): int(offs[k]) + L])
