@@ -120,6 +120,7 @@ struct nwb200_ctx {
     // traceback after a cross-GPU fill: header rows and snapshots in the layout of the whole matrix on every rank (its own column blocks
     // filled in), the other ranks' buffers mapped on the rank that walks the path
     bool wave_keep = false, wave_global = false;
+    int plan_world = 1;                 // ranks the pair being uploaded is spread over (a hint for plan_geometry)
     int scan_warps = 16;                // strips per group of the prefix-max scorer (nw_scan.cuh)
     void* wave_peer_hr[16] = {};
     void* wave_peer_snap[16] = {};

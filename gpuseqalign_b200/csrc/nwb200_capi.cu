@@ -31,7 +31,10 @@ int plan_geometry(nwb200_ctx* c, int n, int m, const nwb200_params* p)
     // one warp per SM sub-partition while that covers all rows; very long pairs take 16 rows per lane (2.7 instead of 3.4 instructions
     // per cell, half as many band hand-offs: 200k^2 fill 13.4 -> 11.6 ms, traceback 2.55 -> 2.8 ms; 300k^2 27.2 -> 25.2 / 4.7 -> 5.4 ms;
     // below ~152k rows the 16-row bands are few enough for the origin maps to ride in the fill launch, which is slow at R = 16)
-    if (R == 0) R = ((long long)n <= 4LL * 32 * 4 * c->sm_count) ? 4 : (n >= 180000 ? 16 : 8);
+    // (across GPUs -- plan_world > 1 -- the critical path through the first band over ALL columns decides, and a step is shorter at R = 8:
+    //  200k^2 on 4 GPUs 15.2 ms per fill + traceback at R = 8 against 18.5 ms at R = 16)
+    if (R == 0) R = ((long long)n <= 4LL * 32 * 4 * c->sm_count) ? 4 : ((n >= 180000 && c->plan_world <= 1) ? 16 : 8);
+    if (!(p && p->rows_per_lane)) { if (const char* e = getenv("NWB200_ROWS_PER_LANE")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) R = v; } }      // developer switch
     if (!(R == 4 || R == 8 || R == 16) || !(W == 1 || W == 4) || Bx < 32 || (Bx % 32) != 0 || Bx > (R == 16 ? 512 : 1024) || !(K == 1 || K == 2))
         return fail(c, NWB200_ERR_INVALID_VALUE, "unsupported tile parameters (rows_per_lane in {4,8,16}, warps_per_block in {1,4}, tile_cols multiple of 32 up to 1024, skew in {1,2})");
     const int By = R * 32;

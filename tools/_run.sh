@@ -1,8 +1,7 @@
-python -m pytest tests/test_gpu_batch.py -m gpu -x -q 2>&1 | tail -2
-for t in 0 1; do
-if [ $t = 1 ]; then export NWB200_BATCH_TICKETS=1; else unset NWB200_BATCH_TICKETS; fi
-python bench.py --steps 20 --warmup 5 --no-secondary --no-cpu-baseline > gpurun_out/r3g_bench_t$t.json 2> gpurun_out/r3g_bench_t$t.err
-python -c "
-import json
-d=json.loads(open('gpurun_out/r3g_bench_t$t.json').read().strip().splitlines()[-1]); print('tickets=$t', round(d['value'],1), round(d['ms_per_step'],4), round(d['roofline']['frac'],4), round(d['e2e']['value'],1), d['e2e']['packed5']['value'], d.get('parity'))"
-done
+run() { timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 tools/wave_trace_check.py "$@" 2> gpurun_out/r3h.err | grep '^{' | python -c "
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); print('R=$NWB200_ROWS_PER_LANE', 'block', d['block'], 'fill rank0', d['fill_ms'], 'fill wall', d['fill_wall_ms'], 'gather+trace wall', d['gather_trace_wall_ms'], 'trace', d['trace_calc_ms'], d['trace_hash'])
+"; }
+export NWB200_ROWS_PER_LANE=8; run 200000 random,random 50176
+export NWB200_ROWS_PER_LANE=16; run 200000 random,random 50176
