@@ -139,7 +139,8 @@ struct nwb200_ctx {
     const char* batch_kernel = "";
     bool batch_packed5 = false;          // the resident batch holds 5-bit packed letters
     int corr_w = 0, corr_nseg = 0;      // the last traceback: segments per band of the corridor pass (0: none) out of corr_nseg
-    int* d_miss = nullptr;              // its miss flag (device)
+    int* d_miss = nullptr;              // its miss flags (device)
+    int corr_levels = 0, corr_w_lv[2] = {0, 0}, corr_d_lv[2] = {0, 0};      // the corridor passes of the last traceback (narrow, wide)
     // resources of the last fill launch (nwb200_get_memory_usage; the reference's updateNwAlgPeakMemUsage, nwalign_shared.cpp:5-25)
     int fill_regs = 0, fill_threads = 0, fill_blocks = 0;
     size_t fill_smem_static = 0, fill_smem_dynamic = 0, fill_local = 0;

@@ -56,10 +56,12 @@ struct TraceArgs {
     // (n, m) to the origin -- corr_w segments per band instead of nseg -- and pass B checks every lookup against that range.  A path
     // that leaves the corridor sets *miss; the full pass A and pass B, enqueued right behind (phase 1), then run -- they return at
     // once otherwise.  The walkers check the result either way (exitj against entry).
-    int corr_w;                      // segments per band of the corridor pass; 0: no corridor
+    int corr_w;                      // segments per band of this pass's corridor; 0: every segment
     int corr_d;                      // half width of the corridor in columns
-    int phase;                       // 0: first pass (the corridor when corr_w > 0), 1: the full pass that runs only after a miss
-    int* miss;
+    int phase;                       // 0: first pass; > 0: a wider corridor / the full pass, which runs only when the pass before it missed
+    int* miss;                       // [0] the pass before this one missed, [1] passes that missed so far (nwb200_trace_info)
+    // A cascade: a narrow corridor, a wide one, everything -- each pass enqueued behind the one before it and returning at once unless
+    // miss[0] is set (the traceback of two unrelated or of two similar 200 000-letter sequences stays within 512 columns of the line).
 };
 
 // Segments [lo, hi] of band b that the corridor pass computes (every segment without a corridor).  Column c of a band's bottom row
@@ -112,8 +114,8 @@ __global__ void __launch_bounds__(WARPS * 32) nw_map_kernel(const TraceArgs a)
     const unsigned ZOFF = (unsigned)a.S * SC::LSTRIDE;
     const long long nwarps = (long long)gridDim.x * WARPS;
     const int nseg = a.nseg;
-    if (a.phase == 1 && __ldcg(a.miss) == 0) return;              // the corridor pass found the whole path
-    const bool corr = a.corr_w > 0 && a.phase == 0;
+    if (a.phase > 0 && __ldcg(a.miss) == 0) return;               // the pass before found the whole path
+    const bool corr = a.corr_w > 0;
     const int per_band = corr ? a.corr_w : nseg;
     const long long nunits = (long long)(a.nb - 1) * per_band;   // band 0 needs no map: the walker of band 0 ends the path itself
     for (long long u = (long long)blockIdx.x * WARPS + w; u < nunits; u += nwarps) {
@@ -201,8 +203,8 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
     __shared__ int wbase[kHopAhead];
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    if (a.phase == 1 && __ldcg(a.miss) == 0) return;          // the corridor pass found the whole path
-    const bool corr = a.corr_w > 0 && a.phase == 0;
+    if (a.phase > 0 && __ldcg(a.miss) == 0) return;           // the pass before found the whole path
+    const bool corr = a.corr_w > 0;
     const int nunits = a.map_half ? 2 * a.nb : a.nb;         // unit u = map row u; the units of band 0 are never looked up
     const int first = a.map_half ? 2 : 1;
     const int wmax = ((a.m + 31) / 32) * 32 - kHopWin;       // last window start that stays inside a map row
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
                     }
                     if (out) {
                         asm volatile("cp.async.wait_all;" ::: "memory");
-                        if (lane == 0) *a.miss = 1;
+                        if (lane == 0) { a.miss[0] = 1; a.miss[1] += 1; }
                         return;
                     }
                     if (jn < 0) jn = 0;               // cannot happen (segment 0 has no cut)
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
         j = jn;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    if (lane == 0) { a.off[a.nb] = off; if (a.phase == 0) *a.miss = 0; }      // (the full pass leaves the flag set: nwb200_trace_info reports it)
+    if (lane == 0) { a.off[a.nb] = off; a.miss[0] = 0; if (a.phase == 0) a.miss[1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------- pass C

@@ -157,10 +157,11 @@ NWB200_API int  nwb200_copy_headers(nwb200_ctx* ctx, int32_t* hrow_host, int32_t
  * the host as they stream back. */
 NWB200_API int  nwb200_score_hash(nwb200_ctx* ctx, uint32_t* score_hash);
 
-/* Diagnostics of the last traceback.  For long pairs the origin maps (pass A of the traceback) are first computed only in a corridor
- * around the straight line from (lenY, lenX) to the origin: *corridor_segments of the *segments map segments per band (0: no corridor
- * pass); *corridor_missed = 1 when the path left the corridor and the full pass ran as well (the result is the same either way).
- * NWB200_CORRIDOR=<half width in columns> overrides the default max(4096, lenX / 32); 0 switches the corridor off. */
+/* Diagnostics of the last traceback.  For long pairs the origin maps (pass A of the traceback) are first computed only in corridors
+ * around the straight line from (lenY, lenX) to the origin -- 1024 columns either side, then max(4096, lenX / 32), then everything:
+ * *corridor_segments of the *segments map segments per band in the first corridor (0: no corridor pass); *corridor_missed = 1 when the
+ * path left every corridor and the full pass ran (the result is the same either way).  NWB200_CORRIDOR=<half width in columns> makes
+ * it one corridor of that width; 0 switches the corridors off. */
 NWB200_API int  nwb200_trace_info(nwb200_ctx* ctx, int* corridor_segments, int* segments, int* corridor_missed);
 
 /* Replaces NwPrintScore2_Sparse's row recomputation (nwtrace2_sparse.cpp:346-419): rows [row0, row0 + nrows) of the

@@ -22,6 +22,7 @@ def main():
     shapes = [(16384, 16384)] if len(sys.argv) < 2 else [tuple(int(v) for v in a.split("x")) for a in sys.argv[1:]]
     for n, m in shapes:
         y = synth.letters(2002, n); x = synth.letters(2001, m)
+        if os.environ.get('MUTATED'): y = synth.mutated_copy(x, 2003, n)
         cfgs = [tuple(int(v) for v in c.split(',')) for c in CONFIGS.split(';')] if CONFIGS else [(0, 0, 0, 0)]
         for (R, W, K, Bx) in cfgs:
             e.upload_pair(y, x, Params(R, W, Bx, K))
@@ -35,7 +36,7 @@ def main():
                     bt = min(bt, e.timing()["trace_calc"])
                 best = min(best, e.timing()["align_calc"])
                 if os.environ.get('VERBOSE'): print(f"   it {it}: fill {e.timing()['align_calc']:.4f}", flush=True)
-            print(f"{n}x{m} R={R} W={W} K={K} Bx={Bx} score={s} fill_ms={best:.4f} GCUPS={n*m/best/1e6:.1f}" + (f" trace_ms={bt:.4f}" if TRACE else ""), flush=True)
+            print(f"{n}x{m} R={R} W={W} K={K} Bx={Bx} score={s} fill_ms={best:.4f} GCUPS={n*m/best/1e6:.1f}" + (f" trace_ms={bt:.4f} {e.trace_info()}" if TRACE else ""), flush=True)
     e.close()
 
 if __name__ == "__main__":
