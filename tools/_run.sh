@@ -1,2 +1,7 @@
-timeout 600 python -m pytest tests/test_gpu_fill.py tests/test_gpu_big.py tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -3
-ITERS=3 TRACE=1 python tools/quick_bench.py 200000x200000 100000x100000 60000x300000 2>&1 | tail -3 | cut -c40-260
+( time python bench.py > gpurun_out/r3k_bench_default.json 2> gpurun_out/r3k_bench_default.err ) 2>&1 | tail -4; echo bench rc=$?
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r3k_bench_default.json').read().strip().splitlines()[-1])
+print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), round(d['roofline']['frac'],4), round(d['e2e']['value'],1), round(d['e2e']['packed5']['value'],1), d.get('parity'))
+for k,v in d.get('secondary',{}).items(): print('  ',k, round(v.get('value'),1), round(v.get('ms_per_step'),3), v.get('laps_ms_last_step'), v.get('traceback'), v.get('parity'))
+PY
