@@ -112,6 +112,7 @@ struct nwb200_ctx {
     nwb::PinBuf h_batch;
     // cross-GPU column-block wavefront
     nwb::DevBuf d_order;             // ticket -> (block round, band) in wavefront order
+    nwb::DevBuf d_corr;              // corridor passes of the traceback: (first, last) segment per band and level
     nwb::DevBuf d_wave;              // [flags (nq+1)*nb | err, pad | recv (nq+1)*recv_stride] -- ONE allocation, exported over CUDA IPC
     void* wave_peer_base = nullptr;  // the right neighbour's d_wave mapped into this process (nullptr: loopback)
     int wave_rank = 0, wave_world = 1, wave_wc = 0, wave_nq = 0, wave_nblocks = 0;

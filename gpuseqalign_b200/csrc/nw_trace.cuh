@@ -59,6 +59,8 @@ struct TraceArgs {
     int corr_w;                      // segments per band of this pass's corridor; 0: every segment
     int corr_d;                      // half width of the corridor in columns
     int phase;                       // 0: first pass; > 0: a wider corridor / the full pass, which runs only when the pass before it missed
+    const int2* corr_tab;            // corridor passes: (first, last) segment of every band, tabulated by the host (the formula has three 64-bit
+                                     // divisions -- a third of the one-warp pointer chase when it ran per band on the device)
     int* miss;                       // [0] the pass before this one missed, [1] passes that missed so far (nwb200_trace_info)
     // A cascade: a narrow corridor, a wide one, everything -- each pass enqueued behind the one before it and returning at once unless
     // miss[0] is set (the traceback of two unrelated or of two similar 200 000-letter sequences stays within 512 columns of the line).
@@ -69,6 +71,9 @@ struct TraceArgs {
 __host__ __device__ __forceinline__ void corridor_range(const TraceArgs& a, int b, int By, int lag, int& lo, int& hi)
 {
     if (a.corr_w <= 0) { lo = 0; hi = a.nseg - 1; return; }
+#ifdef __CUDA_ARCH__
+    if (a.corr_tab != nullptr) { const int2 t = __ldg(a.corr_tab + b); lo = t.x; hi = t.y; return; }
+#endif
     long long rb = (long long)(b + 1) * By - a.pad, rt = (long long)b * By - a.pad;      // matrix rows of the band's last row and of the row above its first
     if (rb > a.n) rb = a.n;
     if (rt < 0) rt = 0;
@@ -201,6 +206,11 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
 {
     __shared__ __align__(16) int win[kHopAhead][kHopWin];
     __shared__ int wbase[kHopAhead];
+    // segmented maps: the cut labels of the segment LEFT of the predicted crossing travel with the window (a path that crosses a cut --
+    // at 512-row bands nearly every band's does -- otherwise pays a dependent L2 load per crossing: 0.61 ms of the 200k^2 traceback)
+    constexpr int kCutMax = 32 * 18;                          // labels per (band, segment): 32 lanes x (R + 2), R <= 16
+    __shared__ __align__(16) int cutwin[kHopAhead][kCutMax];
+    __shared__ int cutseg[kHopAhead];
     if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
     if (a.phase > 0 && __ldcg(a.miss) == 0) return;           // the pass before found the whole path
@@ -223,6 +233,19 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
                 const int e = (i * 32 + lane) * 4;
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&win[slot][e])), "l"(src + e));
             }
+            if (a.cut != nullptr && !a.map_half) {
+                int sgp = (c0 + kHopWin / 2 + cut_lag) / (32 * a.snap_chunks) - 1;      // the segment left of the predicted crossing
+                if (sgp > a.nseg - 2) sgp = a.nseg - 2;
+                if (lane == 0) cutseg[slot] = sgp;
+                if (sgp >= 0) {
+                    const int nlab = 32 * cut_slots;                                     // (a multiple of 4: cut_slots is even)
+                    const int* cs = a.cut + ((long long)u * a.nseg + sgp) * nlab;
+                    for (int e = 4 * lane; e < nlab; e += 128)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&cutwin[slot][e])), "l"(cs + e));
+                }
+            }
+        } else if (lane == 0 && u >= 0) {
+            cutseg[u % kHopAhead] = -1;
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -266,7 +289,9 @@ __global__ void __launch_bounds__(32) nw_hop_kernel(const TraceArgs a, int By, i
                         while (jn < 0 && sg > 0) {
                             sg--;
                             if (sg < lo) { out = true; break; }
-                            jn = __ldcg(a.cut + ((long long)b * a.nseg + sg) * 32 * cut_slots + (-jn - 1));
+                            const int slot = b % kHopAhead;
+                            if (pre && cutseg[slot] == sg) jn = cutwin[slot][-jn - 1];          // (the window's group has landed: lookup waited for it)
+                            else jn = __ldcg(a.cut + ((long long)b * a.nseg + sg) * 32 * cut_slots + (-jn - 1));
                         }
                     }
                     if (out) {

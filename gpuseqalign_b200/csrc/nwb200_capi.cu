@@ -192,7 +192,7 @@ void nwb200_destroy(nwb200_ctx* c)
     }
     for (DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync, &c->d_order,
                       &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
-                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})
+                      &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave, &c->d_corr})
         b->release();
     c->h_stage.release(); c->h_small.release(); c->h_trace.release(); c->h_batch.release(); c->h_export.release();
     c->h_bscores.release(); c->h_bmoves.release();
@@ -501,7 +501,7 @@ int nwb200_get_memory_usage(const nwb200_ctx* c, nwb200_mem_usage* out)
     memset(out, 0, sizeof(*out));
     for (const DevBuf* b : {&c->d_sprime, &c->d_subst, &c->d_y, &c->d_HR, &c->d_snap, &c->d_lastcol, &c->d_sync, &c->d_order,
                             &c->d_map, &c->d_MID, &c->d_tmeta, &c->d_ops, &c->d_dense, &c->d_export, &c->d_HR2, &c->d_cut,
-                            &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave})
+                            &c->d_bletters, &c->d_bmeta, &c->d_bscores, &c->d_bticket, &c->d_bmoves, &c->d_bmoff, &c->d_bcnt, &c->d_dbg, &c->d_wave, &c->d_corr})
         out->device_bytes += b->cap;
     for (const PinBuf* b : {&c->h_stage, &c->h_small, &c->h_trace, &c->h_batch, &c->h_export, &c->h_bscores, &c->h_bmoves}) out->pinned_host_bytes += b->cap;
     out->regs_per_thread = c->fill_regs; out->threads_per_block = c->fill_threads; out->blocks = c->fill_blocks;
