@@ -31,8 +31,10 @@ constexpr int kScanMaxWarps = 16;                       // warps (= strips) per 
                                                         // profiles either way; narrower groups are more CTAs per SM, whose per-row rounds overlap
 constexpr int kScanC = 16;                              // columns per lane
 constexpr int kScanStrip = 32 * kScanC;                 // columns per strip (one warp); a group (the unit the host deals to the ranks) is WARPS strips
-constexpr int kScanAhead = 4;                           // rows the carry of the left group is requested ahead (global memory)
-constexpr int kScanLag = 6;                             // rows a group falls back behind its left neighbour when a request came back empty
+// (1 / 2 rows: one GPU 4.83 -> 4.66 ms for cfg4, 8 GPUs 3.64 -> 2.53 ms -- there every rank has its groups in flight at once and the
+//  start-to-start distance of neighbouring groups, not throughput, sets the time; 4 / 6 rows were the first round-2 values)
+constexpr int kScanAhead = 1;                           // rows the carry of the left group is requested ahead (global memory)
+constexpr int kScanLag = 2;                             // rows a group falls back behind its left neighbour when a request came back empty
 constexpr int kScanRing = 32;                           // rows of the shared-memory rings (strip maxima, group carry)
 __host__ __device__ constexpr size_t scan_warp_smem(int S) { return (size_t)(S + 1) * kScanStrip; }
 __host__ __device__ constexpr size_t scan_cta_smem(int S, int warps) { return (size_t)warps * scan_warp_smem(S) + (size_t)kScanRing * (warps + 1) * 8; }
