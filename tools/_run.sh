@@ -1,7 +1,7 @@
-python -m pytest tests/test_gpu_big.py tests/test_gpu_multi.py -m gpu -x -q -k "prefix or cfg4 or scan" 2>&1 | tail -2
-python bench.py --workload scan4m --steps 10 --warmup 3 --no-secondary --no-cpu-baseline 2>/dev/null | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=1', round(d['value'],1), round(d['ms_per_step'],3), d.get('parity'))"
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --workload scan4m --steps 10 --warmup 3 --no-secondary --no-cpu-baseline 2>/dev/null | grep '^{' | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=2', round(d['value'],1), round(d['ms_per_step'],3), d.get('parity'))"
+python bench.py > gpurun_out/r3p_bench_default.json 2> gpurun_out/r3p_bench_default.err; echo bench rc=$?
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r3p_bench_default.json').read().strip().splitlines()[-1])
+print(d['n_gpus'], round(d['value'],1), round(d['ms_per_step'],4), round(d['roofline']['frac'],4), round(d['e2e']['value'],1), round(d['e2e']['packed5']['value'],1), d.get('parity'))
+for k,v in d.get('secondary',{}).items(): print('  ',k, round(v.get('value'),1), round(v.get('ms_per_step'),3), v.get('parity'))
+PY
