@@ -113,3 +113,52 @@ def test_oracle_vs_live_reference_when_present(golden, scoring, oracle):
         score, hrow, hcol, _ = oracle.fill_rolling(y, x, subst, -11, 128, 209)
         r2 = oracle.ref_trace_from_headers(y, x, subst, -11, hrow, hcol, 128, 209, want_hash=True)
         assert (r2.score, r2.score_hash, r2.trace_hash, r2.edit) == (ref.score, ref.score_hash, ref.trace_hash, ref.edit)
+
+
+def _gotoh_py(y, x, subst, S, go, ge, local):
+    """Independent pure-Python Gotoh (three explicit matrices, no rolling rows): the textbook recurrence the C restatement
+    (nwo_score_batch_gotoh) and the GPU kernel implement; a gap of L residues costs go + (L - 1) * ge."""
+    NEG = -10 ** 9
+    n, m = len(y), len(x)
+    H = [[0] * (m + 1) for _ in range(n + 1)]
+    E = [[NEG] * (m + 1) for _ in range(n + 1)]
+    F = [[NEG] * (m + 1) for _ in range(n + 1)]
+    if not local:
+        for i in range(1, n + 1): H[i][0] = go + (i - 1) * ge
+        for j in range(1, m + 1): H[0][j] = go + (j - 1) * ge
+    best = 0
+    for i in range(1, n + 1):
+        for j in range(1, m + 1):
+            E[i][j] = max(E[i][j - 1] + ge, H[i][j - 1] + go)
+            F[i][j] = max(F[i - 1][j] + ge, H[i - 1][j] + go)
+            h = max(H[i - 1][j - 1] + int(subst[int(y[i - 1]) * S + int(x[j - 1])]), E[i][j], F[i][j])
+            if local: h = max(h, 0)
+            H[i][j] = h
+            best = max(best, h)
+    return best if local else H[n][m]
+
+
+def test_gotoh_restatement_against_an_independent_implementation(oracle, scoring):
+    """The affine-gap / Smith-Waterman restatement (parity unpinned: the reference implements neither) against a pure-Python textbook
+    Gotoh on small ragged pairs, and its one pinned case: gap_extend == gap_open is the reference's linear-gap recurrence."""
+    subst = scoring["subst"]["blosum62"]
+    S = int(round(len(subst) ** 0.5))
+    rng = np.random.default_rng(11)
+    n = 40
+    lenY = rng.integers(0, 30, n).astype(np.uint32); lenX = rng.integers(0, 30, n).astype(np.uint32)
+    lens = np.empty(2 * n, dtype=np.uint64); lens[0::2] = lenY; lens[1::2] = lenX
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    letters = rng.integers(0, 24, int(offs[-1]) + 1).astype(np.uint8)
+    offY, offX = offs[0:-1:2].copy(), offs[1::2].copy()
+    for go, ge, local in ((-11, -1, False), (-5, -3, False), (-11, -1, True), (-11, -11, True), (-4, 0, True), (-7, -7, False)):
+        got = oracle.score_batch_gotoh(letters, offY, lenY, offX, lenX, subst, go, ge, local)
+        for p in range(n):
+            y = letters[int(offY[p]): int(offY[p]) + int(lenY[p])]; x = letters[int(offX[p]): int(offX[p]) + int(lenX[p])]
+            if len(y) == 0 or len(x) == 0:
+                k = len(y) + len(x)
+                exp = 0 if (local or k == 0) else go + (k - 1) * ge
+            else:
+                exp = _gotoh_py(y, x, subst, S, go, ge, local)
+            assert got[p] == exp, (go, ge, local, p, len(y), len(x))
+    assert np.array_equal(oracle.score_batch_gotoh(letters, offY, lenY, offX, lenX, subst, -11, -11, False),
+                          oracle.score_batch(letters, offY, lenY, offX, lenX, subst, -11))
