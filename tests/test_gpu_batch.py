@@ -95,7 +95,7 @@ def test_batch_pinned_and_pageable_sources_agree(engine, scoring, oracle):
     assert int(a.astype(np.int64).sum()) == int(b.astype(np.int64).sum())
 
 
-@pytest.mark.parametrize("n_pairs,max_y,max_x", [(1, 256, 256), (7, 128, 200), (601, 256, 300), (333, 100, 60)])
+@pytest.mark.parametrize("n_pairs,max_y,max_x", [(1, 256, 256), (7, 128, 200), (601, 256, 300), (333, 100, 60), (90, 500, 300)])
 def test_batch_packed_and_32bit_kernels_agree(engine, scoring, oracle, monkeypatch, n_pairs, max_y, max_x):
     """Two pairs per warp in 16-bit halves (nw_batch2.cuh) vs one pair per warp (nw_batch.cuh) vs the oracle: odd pair
     counts (a warp whose second half is empty), both band heights, ragged partners in one warp."""
