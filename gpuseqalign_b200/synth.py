@@ -90,17 +90,21 @@ def pack5(letters: np.ndarray, offs: np.ndarray, lens: np.ndarray):
     out = np.zeros(total + 64, dtype=np.uint8)
     if lens.size == 0:
         return out, new_offs
-    if np.all(lens == lens[0]) and lens[0] % 8 == 0 and lens[0] > 0:      # equal lengths, whole groups of 8 letters: one vectorised pass
+    if np.all(lens == lens[0]) and lens[0] % 8 == 0 and lens[0] > 0:      # equal lengths, whole groups of 8 letters: vectorised, in slabs
         L = int(lens[0])
-        idx = offs[:, None] + np.arange(L, dtype=np.int64)[None, :]
-        v = letters[idx].reshape(lens.size, L // 8, 8).astype(np.uint64)
-        word = np.zeros((lens.size, L // 8), dtype=np.uint64)
-        for k in range(8):
-            word |= (v[:, :, k] & np.uint64(31)) << np.uint64(5 * k)
-        b = np.empty((lens.size, L // 8, 5), dtype=np.uint8)
-        for k in range(5):
-            b[:, :, k] = ((word >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
-        out[:total] = b.reshape(-1)
+        per = L // 8 * 5                                                   # packed bytes per sequence
+        ar = np.arange(L, dtype=np.int64)[None, :]
+        slab = max(1, (1 << 24) // L)                                       # ~16 M letters (a few hundred MB of temporaries) at a time
+        for lo in range(0, lens.size, slab):
+            hi = min(lens.size, lo + slab)
+            v = letters[offs[lo:hi, None] + ar].reshape(hi - lo, L // 8, 8)
+            word = np.zeros((hi - lo, L // 8), dtype=np.uint64)
+            for k in range(8):
+                word |= (v[:, :, k].astype(np.uint64) & np.uint64(31)) << np.uint64(5 * k)
+            b = np.empty((hi - lo, L // 8, 5), dtype=np.uint8)
+            for k in range(5):
+                b[:, :, k] = ((word >> np.uint64(8 * k)) & np.uint64(255)).astype(np.uint8)
+            out[lo * per: hi * per] = b.reshape(-1)
         return out, new_offs
     for k in range(lens.size):                                             # ragged: sequence by sequence
         L = int(lens[k])
