@@ -1,4 +1,7 @@
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --workload wave200k --steps 5 --warmup 2 --no-secondary --no-cpu-baseline 2> gpurun_out/r3q.err | grep '^{' | python -c "
-import sys, json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('N=8', round(d['value'],1), round(d['ms_per_step'],3), d['roofline'].get('laps_ms_last_step'), d['roofline'].get('traceback'), d.get('parity')); open('gpurun_out/r3q_bench_wave200k_N8.json','w').write(json.dumps(d))"
-tail -2 gpurun_out/r3q.err | cut -c1-200
+# scratch script sent to the GPU box by `gpurun -- 'bash tools/_run.sh'` (rewritten per experiment); the validation run of a build:
+python -m pytest tests -m gpu -x -q | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" | tail -1
+python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo bench rc=$?
+python -c "
+import json
+d=json.loads(open('gpurun_out/bench_default.json').read().strip().splitlines()[-1]); print(round(d['value'],1), round(d['roofline']['frac'],4), round(d['e2e']['value'],1), d.get('parity')); print({k:(round(v['value'],1), v.get('parity')) for k,v in d['secondary'].items()})"
