@@ -80,3 +80,76 @@ def test_two_rank_sharded_batch_equals_unsharded(oracle):
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res)
     assert sum(k for _, _, k in res) == 301
+
+
+class _FakeWaveEngine:
+    """Stand-in for Engine in the CPU test of the cross-GPU host choreography (gpuseqalign_b200/wavefront.py): records the calls,
+    hands out recognisable 64-byte handles, and plays a corridor miss on the first traceback when asked to."""
+
+    def __init__(self, rank, miss_first=False):
+        self.rank, self.calls, self.miss_first, self.traces = rank, [], miss_first, 0
+
+    def wave_keep_headers(self, on=True): self.calls.append(("keep", bool(on)))
+    def wave_upload(self, y, x, rank, world, block_cols, params=None):
+        self.calls.append(("upload", rank, world, block_cols)); return bytes([rank]) * 64
+    def scan_upload(self, y, x, rank, world):
+        self.calls.append(("scan_upload", rank, world)); return bytes([100 + rank]) * 64
+    def wave_connect(self, h): self.calls.append(("connect", None if h is None else h[0]))
+    def wave_export_headers(self): return bytes([10 + self.rank]) * 64, bytes([20 + self.rank]) * 64
+    def wave_connect_headers(self, hr, sn): self.calls.append(("connect_headers", [h[0] for h in hr], [h[0] for h in sn]))
+    def wave_fill(self, epoch): self.calls.append(("fill", epoch))
+    def scan_fill(self, epoch): self.calls.append(("scan_fill", epoch))
+    def wave_fetch(self): return 1234 if self.rank == 1 else None            # the owner of the last block has the score
+    def scan_fetch(self): return 777 if self.rank == 1 else None
+    def wave_gather_headers(self, full=False): self.calls.append(("gather", bool(full)))
+    def trace_resident(self): self.traces += 1; self.calls.append(("trace",))
+    def trace_info(self): return {"corridor_segments": 6, "segments": 100, "corridor_missed": self.miss_first and self.traces == 1}
+    def fetch_trace(self, cap=0): return "3=1X", 0xabcdef
+
+
+def _wave_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from gpuseqalign_b200.wavefront import wave_align, scan_align, wave_trace_setup, wave_trace
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        y = np.zeros(10, np.uint8); x = np.zeros(20, np.uint8)
+        e = _FakeWaveEngine(rank)
+        s1 = wave_align(e, y, x, rank=rank, world=world, block_cols=64, epoch=5)
+        s2 = scan_align(e, y, x, rank=rank, world=world, epoch=6)
+        e2 = _FakeWaveEngine(rank, miss_first=True)
+        wave_trace_setup(e2, y, x, rank=rank, world=world, block_cols=512)
+        e2.wave_fill(7); e2.wave_fetch()
+        tr = wave_trace(e2, rank=rank, world=world)
+        q.put((rank, s1, s2, e.calls, e2.calls, tr))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_wavefront_choreography():
+    """wave_align / scan_align / wave_trace_setup / wave_trace over gloo with a stand-in engine: every rank maps its RIGHT neighbour's
+    receive buffer, every rank gets the score of the last block's owner, only the tracer maps the header buffers, gathers and walks --
+    and after a corridor miss gathers everything and walks again -- and nobody is left waiting in a collective."""
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_wave_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, s1, s2, calls, calls2, tr in res:
+        assert (s1, s2) == (1234, 777)
+        assert ("connect", (rank + 1) % 2) in calls and ("fill", 5) in calls                    # the right neighbour's wave buffer
+        assert ("connect", 100 + (rank + 1) % 2) in calls and ("scan_fill", 6) in calls        # ... and its scan buffer
+        assert calls2[0] == ("keep", True) and ("keep", False) in calls2 and ("upload", rank, 2, 512) in calls2
+        if rank == 0:
+            assert ("connect_headers", [10, 11], [20, 21]) in calls2
+            assert [c for c in calls2 if c[0] in ("gather", "trace")] == [("gather", False), ("trace",), ("gather", True), ("trace",)]
+            assert tr[0] == "3=1X" and tr[1] == 0xabcdef and tr[2]["corridor_missed"]
+        else:
+            assert tr is None and not any(c[0] in ("gather", "trace", "connect_headers") for c in calls2)
